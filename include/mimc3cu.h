@@ -1,0 +1,170 @@
+/* mimc3cu -- C ABI of the B200-native MIMC3 matching library (libmimc3cu.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch or C++ types.  It
+ * replaces the reference translation unit MIMC_module.c.  Two layers:
+ *
+ *   1. mimc3cu_*  (this header): explicit, handle-based API used by tests, bench.py and
+ *      by layer 2.  Each entry point cites the reference function it replaces.
+ *   2. The five MIMC_module.h entry points themselves (get_offset_image, get_uv_pivot,
+ *      matching_ncc_dlc_2, GMA_float_conv2, mimc2_postprocess), implemented over layer 1
+ *      in mimc3_b200/csrc/dropin.c so that the reference's unchanged MIMC_main.c links
+ *      against this library instead of MIMC_module.c.
+ *
+ * Conventions
+ *   - Images are row-major float32 (H rows, W columns), exactly the payload of the
+ *     reference's GMA_float (GMA.h:73-80).
+ *   - xyuvav is row-major float64 (n, 6): x, y, u, v, vx, vy (MIMC_main.c:203, README.md:36).
+ *   - Pivots are CSR: off[n+1] (int32) + piv[total][2] (int32 u, v), replacing the ragged
+ *     GMA_int32** of MIMC_module.h:39.
+ *   - dp ("displacement") arrays are (n, 3) float32 [du, dv, ncc] as returned by
+ *     matching_ncc_dlc_2 (MIMC_module.c:805-842).
+ *   - All functions return 0 on success, non-zero on error; mimc3cu_last_error() gives
+ *     the message.  There is NO CPU fallback: without a CUDA device every compute entry
+ *     point fails.
+ *   - Calls are synchronous with respect to the host unless the name ends in _async;
+ *     device work is issued on the context's stream (mimc3cu_stream).
+ */
+#ifndef MIMC3CU_H
+#define MIMC3CU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MIMC3CU_VERSION 100
+
+typedef struct mimc3cu_ctx mimc3cu_ctx;
+
+/* Parameters the reference hard-codes in MIMC_main.c:134-168 / derives at :221-223. */
+typedef struct mimc3cu_params {
+    int32_t vec_ocw[4];          /* chip half-widths {7,15,30,40}          MIMC_main.c:134-137 */
+    float AW_CRE;                /* 10                                      :153 */
+    float AW_SF;                 /* 1.8                                     :154 */
+    float mpp;                   /* metres per pixel                        :221 */
+    float meter_per_spacing;     /*                                         :223 */
+    float radius_neighbor_dpf1;  /* 1000/300 = 3 (integer division)         :161 */
+    float radius_neighbor_ps;    /* 5                                       :162 */
+    float dt;                    /* days between the images                 :114 */
+    int32_t dimx, dimy;          /* node grid                               :211-219 */
+    int32_t num_dp;              /* attempts per node (32)                  :74 */
+} mimc3cu_params;
+
+void mimc3cu_default_params(mimc3cu_params *p);
+
+/* ---- context ------------------------------------------------------------------ */
+int mimc3cu_version(void);
+/* Number of CUDA devices visible (0 => every compute call will fail). */
+int mimc3cu_device_count(void);
+int mimc3cu_create(int device, mimc3cu_ctx **ctx);
+void mimc3cu_destroy(mimc3cu_ctx *ctx);
+const char *mimc3cu_last_error(const mimc3cu_ctx *ctx); /* ctx may be NULL: global error */
+/* cudaStream_t of the context as an opaque pointer (for event timing by the caller). */
+void *mimc3cu_stream(mimc3cu_ctx *ctx);
+int mimc3cu_sync(mimc3cu_ctx *ctx);
+/* Kernel launches issued by this context since creation (for the bench's gpu_launches). */
+int64_t mimc3cu_launch_count(const mimc3cu_ctx *ctx);
+
+/* ---- images (replace GMA_float payloads living in host RAM) --------------------- */
+/* Allocate an (H, W) float32 image in HBM, zero-initialised (the
+ * reference's conv2 output buffers behave as zero-initialised memory). */
+int mimc3cu_image_create(mimc3cu_ctx *ctx, int32_t H, int32_t W, int32_t *handle);
+int mimc3cu_image_destroy(mimc3cu_ctx *ctx, int32_t handle);
+/* Host -> HBM (pageable or pinned host memory). */
+int mimc3cu_image_upload(mimc3cu_ctx *ctx, int32_t handle, const float *host);
+/* u8 / u16 -> f32 cast on the device: GMA_float_load_tiff's per-pixel loop, GMA.c:288-310. */
+int mimc3cu_image_upload_u8(mimc3cu_ctx *ctx, int32_t handle, const uint8_t *host);
+int mimc3cu_image_upload_u16(mimc3cu_ctx *ctx, int32_t handle, const uint16_t *host);
+/* Device -> device copy from a caller-owned device buffer (e.g. a torch tensor). */
+int mimc3cu_image_copy_from_device(mimc3cu_ctx *ctx, int32_t handle, const float *dev);
+int mimc3cu_image_download(mimc3cu_ctx *ctx, int32_t handle, float *host);
+/* Raw device pointer of the image payload. */
+float *mimc3cu_image_ptr(mimc3cu_ctx *ctx, int32_t handle);
+
+/* GMA_float_conv2, MIMC_module.c:2517-2585.  dst is updated IN PLACE with the
+ * reference's stale-border semantics.  kernel is (kh, kw) row-major
+ * float32 on the host; kh, kw in {1, 3}. */
+int mimc3cu_conv2(mimc3cu_ctx *ctx, int32_t src, const float *kernel, int32_t kh, int32_t kw, int32_t dst);
+
+/* ---- nodes and pivots ----------------------------------------------------------- */
+/* get_uv_pivot, MIMC_module.c:543-602 (host code in the reference too: libm trig,
+ * ragged output).  Multi-threaded host implementation, bit-identical including the
+ * |cos|>|sin| normalisation quirk.  Two-call protocol: pass piv == NULL to obtain the
+ * offsets and the total; then call again with piv sized total*2. Returns total (<0: error). */
+int64_t mimc3cu_get_uv_pivot(const double *xyuvav, int32_t n, float dt, float mpp, float AW_SF, float AW_CRE,
+                             int32_t ocw, int32_t H, int32_t W, int32_t *off, int32_t *piv);
+
+/* Upload the node list (columns 2,3 truncated to int32 as at MIMC_module.c:822-823). */
+int mimc3cu_set_nodes(mimc3cu_ctx *ctx, const double *xyuvav, int32_t n);
+/* Upload a CSR pivot set into slot `slot` (0..7); the library keeps it in HBM. */
+int mimc3cu_set_pivots(mimc3cu_ctx *ctx, int32_t slot, const int32_t *off, const int32_t *piv, int32_t n);
+
+/* ---- the matcher ---------------------------------------------------------------- */
+/* matching_ncc_dlc_2 (+extract_refchip, extract_sarea, investigate_valid_grid,
+ * find_ncc_peak), MIMC_module.c:605-890, for all nodes set by mimc3cu_set_nodes.
+ *   ref_img/search_img : image handles (i0,i1 for the forward pass; swapped for the
+ *                        "swapped forward" pass, MIMC_main.c:267,284)
+ *   offset[2]          : CP integer offset added to the node position in the search image
+ *   pivot_slot, sign   : pivot set; sign=-1 reproduces main's in-place negation (:272-279)
+ *   negate_duv         : multiply du,dv of the result by -1 (main does this to the swapped
+ *                        pass on the host, :289-293)
+ * Outputs are DEVICE pointers (any may be NULL except dp): dp (n,3) f32, peak (n,2) i32
+ * integer peak relative to the search-area centre, ncell (n) i32 number of NCC cells the
+ * reference algorithm evaluates (E in SURVEY.md 8d). Asynchronous on the context stream. */
+int mimc3cu_match_async(mimc3cu_ctx *ctx, int32_t ref_img, int32_t search_img, const int32_t *offset,
+                        int32_t pivot_slot, int32_t sign, int32_t ocw, int32_t negate_duv,
+                        float *dp_dev, int32_t *peak_dev, int32_t *ncell_dev);
+/* Same, synchronous, results copied to HOST buffers. */
+int mimc3cu_match(mimc3cu_ctx *ctx, int32_t ref_img, int32_t search_img, const int32_t *offset,
+                  int32_t pivot_slot, int32_t sign, int32_t ocw, int32_t negate_duv,
+                  float *dp_host, int32_t *peak_host, int32_t *ncell_host);
+
+/* find_ncc_peak on explicit chips (the CP stage's call shape, MIMC_module.c:351,369):
+ * `count` independent problems; refchips (count, S, S), sareas (count, D, D) float32 on
+ * the HOST, one shared pivot list (P,2).  Results to host: uvncc (count,3), peak (count,2). */
+int mimc3cu_find_ncc_peak_batch(mimc3cu_ctx *ctx, const float *refchips, int32_t S, const float *sareas,
+                                int32_t D, int32_t count, const int32_t *piv, int32_t P,
+                                float *uvncc_host, int32_t *peak_host, int32_t *ncell_host);
+
+/* The whole multi-match of MIMC_main.c:261-350: 4 chip sizes x {forward, swapped} on the
+ * raw pair, then on the three conv2-filtered pairs => 32 dp arrays, stored attempt-major
+ * in dp_dev (32, n, 3) on the DEVICE.  Pivots for the 4 chip sizes must be in slots 0..3.
+ * ncell_dev (32, n) optional. i0c/i1c are scratch images for the filtered pair. */
+int mimc3cu_multimatch_async(mimc3cu_ctx *ctx, int32_t i0, int32_t i1, int32_t i0c, int32_t i1c,
+                             const int32_t *offset, const mimc3cu_params *p, float *dp_dev, int32_t *ncell_dev);
+
+/* ---- postprocess ---------------------------------------------------------------- */
+/* calc_mean_var_num_dp_cluster, MIMC_module.c:994-1194: dp_dev (num_dp, n, 3) ->
+ * mvn_dev (n, num_dp, 5) [mean u, mean v, var u, var v, support], ncl_dev (n). */
+int mimc3cu_cluster_async(mimc3cu_ctx *ctx, const float *dp_dev, int32_t n, int32_t num_dp,
+                          float *mvn_dev, int32_t *ncl_dev);
+
+/* mimc2_postprocess, MIMC_module.c:893-991 (cluster -> dpf0 -> dpf1 sweeps -> 3x3
+ * smoothing -> snap -> pseudosmoothing -> pack): dp_dev (num_dp, n, 3) on the device,
+ * xyuvav (n,6) on the host -> planes_dev 5 x (dimy, dimx) f32 on the device
+ * [du, dv, var u, var v, support].  stats (optional, host, 4 ints): dpf1 sweeps,
+ * pseudosmoothing sweeps, holes after dpf0, nodes changed by pseudosmoothing. */
+int mimc3cu_postprocess(mimc3cu_ctx *ctx, const float *dp_dev, const double *xyuvav, const mimc3cu_params *p,
+                        float *planes_dev, int32_t *stats);
+
+/* Intermediate fields of the last mimc3cu_postprocess call, copied to the host for the
+ * differential tests: which = 0 dpf0 (i32), 1 dpf1 ids (i32), 2 dpf1 dx (f32), 3 dpf1 dy,
+ * 4 pseudosmoothing ids, 5 ps dx, 6 ps dy, 7 ncl (i32). `host` holds n 4-byte values. */
+int mimc3cu_postprocess_stage(mimc3cu_ctx *ctx, int32_t which, void *host);
+
+/* main()'s tail, MIMC_main.c:356-402: mean of the non-NaN du,dv removed (sequential
+ * float sums), px -> m/yr, vy sign flip, sqrt of the variances. In place on planes_dev. */
+int mimc3cu_finalize(mimc3cu_ctx *ctx, float *planes_dev, const mimc3cu_params *p, float *du_cp, float *dv_cp);
+
+/* ---- device memory helpers (so a plain-C host needs no CUDA headers) -------------- */
+int mimc3cu_malloc(mimc3cu_ctx *ctx, size_t bytes, void **dev);
+int mimc3cu_free(mimc3cu_ctx *ctx, void *dev);
+int mimc3cu_memcpy_d2h(mimc3cu_ctx *ctx, void *host, const void *dev, size_t bytes);
+int mimc3cu_memcpy_h2d(mimc3cu_ctx *ctx, void *dev, const void *host, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MIMC3CU_H */

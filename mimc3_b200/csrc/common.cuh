@@ -1,0 +1,107 @@
+// Internal declarations shared by the translation units of libmimc3cu.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/mimc3cu.h"
+
+#define MIMC3CU_MAX_PIVOT_SLOTS 8
+
+struct Image {
+    float *d = nullptr;
+    int32_t H = 0, W = 0;
+    bool used = false;
+};
+
+struct PivotSet {
+    int32_t *off = nullptr;    // device, n+1
+    int32_t *piv = nullptr;    // device, total*2
+    int32_t n = 0;
+    int64_t total = 0;
+    int32_t max_abs_u = 0, max_abs_v = 0;   // over the last pivot of every node
+    int64_t max_cells = 0;                  // max (2|ul|+4)(2|vl|+4): reachable cmap region
+    int64_t max_sarea_extra = 0;            // helper: max over nodes of (|ul|+2, |vl|+2) product terms
+    std::vector<int32_t> last_u, last_v;    // host copy of |last pivot| per node (for smem sizing)
+};
+
+struct mimc3cu_ctx {
+    int device = 0;
+    int num_sms = 0;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+
+    std::vector<Image> images;
+
+    // nodes
+    int32_t n = 0;
+    int2 *node_uv = nullptr;     // device (n)
+    double *xyuvav_d = nullptr;  // device (n,6)
+
+    PivotSet pivots[MIMC3CU_MAX_PIVOT_SLOTS];
+
+    // matcher scratch
+    void *scratch = nullptr;
+    size_t scratch_bytes = 0;
+    unsigned int *counter = nullptr;   // dynamic node fetch
+    float *minbuf = nullptr;           // conv2 reduction
+
+    // postprocess state kept for mimc3cu_postprocess_stage
+    struct Post *post = nullptr;
+};
+
+extern std::string g_mimc3cu_error;
+
+int mimc3cu_fail(mimc3cu_ctx *ctx, const char *fmt, ...);
+
+#define CU_CHECK(ctx, call)                                                                         \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return mimc3cu_fail(ctx, "%s:%d: %s failed: %s", __FILE__, __LINE__, #call,             \
+                                cudaGetErrorString(e__));                                           \
+    } while (0)
+
+int ensure_scratch(mimc3cu_ctx *ctx, size_t bytes);
+Image *get_image(mimc3cu_ctx *ctx, int32_t handle);
+
+// match.cu
+struct MatchLaunch {
+    // image mode
+    const float *ref = nullptr, *srch = nullptr;
+    int32_t H = 0, W = 0;
+    const int2 *node_uv = nullptr;
+    int32_t off_u = 0, off_v = 0;
+    const int32_t *csr_off = nullptr;   // NULL => shared pivot list (explicit mode)
+    const int32_t *piv = nullptr;
+    int32_t sign = 1;
+    // explicit mode (CP stage)
+    const float *chips = nullptr, *sareas = nullptr;
+    int32_t D = 0, P = 0;
+    // common
+    int32_t n = 0, ocw = 0;
+    float negate = 1.0f;
+    float *dp = nullptr;
+    int32_t *peak = nullptr, *ncell = nullptr;
+    int64_t max_cells = 0;       // reachable cmap cells, max over nodes
+    int64_t max_sarea = 0;       // Dx2*Dy2, max over nodes
+};
+int launch_match(mimc3cu_ctx *ctx, const MatchLaunch &L);
+
+// conv2.cu
+int launch_conv2(mimc3cu_ctx *ctx, const float *src, int32_t H, int32_t W, const float *kernel, int32_t kh,
+                 int32_t kw, float *dst);
+int launch_cast_u8(mimc3cu_ctx *ctx, const uint8_t *src, float *dst, size_t count);
+int launch_cast_u16(mimc3cu_ctx *ctx, const uint16_t *src, float *dst, size_t count);
+
+// post.cu
+int post_cluster(mimc3cu_ctx *ctx, const float *dp, int32_t n, int32_t num_dp, float *mvn, int32_t *ncl);
+int post_run(mimc3cu_ctx *ctx, const float *dp, const double *xyuvav_host, const mimc3cu_params *p, float *planes,
+             int32_t *stats);
+int post_stage(mimc3cu_ctx *ctx, int32_t which, void *host);
+int post_finalize(mimc3cu_ctx *ctx, float *planes, const mimc3cu_params *p, float *du_cp, float *dv_cp);
+void post_free(mimc3cu_ctx *ctx);

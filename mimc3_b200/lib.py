@@ -1,0 +1,281 @@
+"""ctypes binding of libmimc3cu.so (include/mimc3cu.h) -- the product's Python host layer.
+
+The library is the product; this module only marshals numpy / torch buffers into the
+C ABI.  There is no CPU fallback: `Context()` raises if the shared library is missing or
+no sm_100 device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmimc3cu.so")
+
+
+class Mimc3CuError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    """mimc3cu_params (include/mimc3cu.h) == the reference's hard-coded MIMC_main.c:134-168."""
+    _fields_ = [("vec_ocw", C.c_int32 * 4), ("AW_CRE", C.c_float), ("AW_SF", C.c_float), ("mpp", C.c_float),
+                ("meter_per_spacing", C.c_float), ("radius_neighbor_dpf1", C.c_float),
+                ("radius_neighbor_ps", C.c_float), ("dt", C.c_float), ("dimx", C.c_int32), ("dimy", C.c_int32),
+                ("num_dp", C.c_int32)]
+
+
+_lib = None
+
+
+def load_library(path: str = LIB_PATH) -> C.CDLL:
+    """Load libmimc3cu.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(path):
+        raise Mimc3CuError(f"{path} is missing: run `python -m mimc3_b200.build` (nvcc, sm_100a). "
+                           "There is no CPU fallback.")
+    L = C.CDLL(path)
+    vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+    sigs = {
+        "mimc3cu_default_params": (None, [C.POINTER(Params)]),
+        "mimc3cu_version": (C.c_int, []),
+        "mimc3cu_device_count": (C.c_int, []),
+        "mimc3cu_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+        "mimc3cu_destroy": (None, [vp]),
+        "mimc3cu_last_error": (C.c_char_p, [vp]),
+        "mimc3cu_stream": (vp, [vp]),
+        "mimc3cu_sync": (C.c_int, [vp]),
+        "mimc3cu_launch_count": (i64, [vp]),
+        "mimc3cu_image_create": (C.c_int, [vp, i32, i32, C.POINTER(i32)]),
+        "mimc3cu_image_destroy": (C.c_int, [vp, i32]),
+        "mimc3cu_image_upload": (C.c_int, [vp, i32, vp]),
+        "mimc3cu_image_upload_u8": (C.c_int, [vp, i32, vp]),
+        "mimc3cu_image_upload_u16": (C.c_int, [vp, i32, vp]),
+        "mimc3cu_image_copy_from_device": (C.c_int, [vp, i32, vp]),
+        "mimc3cu_image_download": (C.c_int, [vp, i32, vp]),
+        "mimc3cu_image_ptr": (vp, [vp, i32]),
+        "mimc3cu_conv2": (C.c_int, [vp, i32, vp, i32, i32, i32]),
+        "mimc3cu_get_uv_pivot": (i64, [vp, i32, f32, f32, f32, f32, i32, i32, i32, vp, vp]),
+        "mimc3cu_set_nodes": (C.c_int, [vp, vp, i32]),
+        "mimc3cu_set_pivots": (C.c_int, [vp, i32, vp, vp, i32]),
+        "mimc3cu_match_async": (C.c_int, [vp, i32, i32, vp, i32, i32, i32, i32, vp, vp, vp]),
+        "mimc3cu_match": (C.c_int, [vp, i32, i32, vp, i32, i32, i32, i32, vp, vp, vp]),
+        "mimc3cu_find_ncc_peak_batch": (C.c_int, [vp, vp, i32, vp, i32, i32, vp, i32, vp, vp, vp]),
+        "mimc3cu_multimatch_async": (C.c_int, [vp, i32, i32, i32, i32, vp, C.POINTER(Params), vp, vp]),
+        "mimc3cu_cluster_async": (C.c_int, [vp, vp, i32, i32, vp, vp]),
+        "mimc3cu_postprocess": (C.c_int, [vp, vp, vp, C.POINTER(Params), vp, vp]),
+        "mimc3cu_postprocess_stage": (C.c_int, [vp, i32, vp]),
+        "mimc3cu_finalize": (C.c_int, [vp, vp, C.POINTER(Params), C.POINTER(f32), C.POINTER(f32)]),
+        "mimc3cu_malloc": (C.c_int, [vp, C.c_size_t, C.POINTER(vp)]),
+        "mimc3cu_free": (C.c_int, [vp, vp]),
+        "mimc3cu_memcpy_d2h": (C.c_int, [vp, vp, vp, C.c_size_t]),
+        "mimc3cu_memcpy_h2d": (C.c_int, [vp, vp, vp, C.c_size_t]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    L._mimc3cu_symbols = tuple(sigs)
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = (
+    "mimc3cu_default_params", "mimc3cu_version", "mimc3cu_device_count", "mimc3cu_create", "mimc3cu_destroy",
+    "mimc3cu_last_error", "mimc3cu_stream", "mimc3cu_sync", "mimc3cu_launch_count", "mimc3cu_image_create",
+    "mimc3cu_image_destroy", "mimc3cu_image_upload", "mimc3cu_image_upload_u8", "mimc3cu_image_upload_u16",
+    "mimc3cu_image_copy_from_device", "mimc3cu_image_download", "mimc3cu_image_ptr", "mimc3cu_conv2",
+    "mimc3cu_get_uv_pivot", "mimc3cu_set_nodes", "mimc3cu_set_pivots", "mimc3cu_match_async", "mimc3cu_match",
+    "mimc3cu_find_ncc_peak_batch", "mimc3cu_multimatch_async", "mimc3cu_cluster_async", "mimc3cu_postprocess",
+    "mimc3cu_postprocess_stage", "mimc3cu_finalize", "mimc3cu_malloc", "mimc3cu_free", "mimc3cu_memcpy_d2h",
+    "mimc3cu_memcpy_h2d",
+)
+
+
+def _ptr(a):
+    """Address of a numpy array / torch tensor / int / None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        assert a.flags.c_contiguous
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        assert a.is_contiguous()
+        return a.data_ptr()
+    raise TypeError(type(a))
+
+
+def default_params() -> Params:
+    p = Params()
+    load_library().mimc3cu_default_params(C.byref(p))
+    return p
+
+
+def params_for(xyuvav: np.ndarray, dimx: int, dimy: int, dt: float) -> Params:
+    """What main derives from the xyuvav matrix, MIMC_main.c:211-223."""
+    p = default_params()
+    p.mpp = np.float32((xyuvav[1, 0] - xyuvav[0, 0]) / (xyuvav[1, 2] - xyuvav[0, 2]))
+    p.meter_per_spacing = np.float32(xyuvav[1, 0] - xyuvav[0, 0])
+    p.dt = np.float32(dt)
+    p.dimx, p.dimy = dimx, dimy
+    return p
+
+
+def get_uv_pivot(xyuvav, dt, mpp, ocw, H, W, aw_sf=1.8, aw_cre=10.0):
+    """get_uv_pivot (MIMC_module.c:543-602) -> CSR (off[n+1], piv[total,2])."""
+    L = load_library()
+    x = np.ascontiguousarray(xyuvav, dtype=np.float64)
+    n = x.shape[0]
+    off = np.zeros(n + 1, np.int32)
+    tot = L.mimc3cu_get_uv_pivot(_ptr(x), n, dt, mpp, aw_sf, aw_cre, ocw, H, W, _ptr(off), None)
+    if tot < 0:
+        raise Mimc3CuError(L.mimc3cu_last_error(None).decode())
+    piv = np.zeros((max(tot, 1), 2), np.int32)
+    L.mimc3cu_get_uv_pivot(_ptr(x), n, dt, mpp, aw_sf, aw_cre, ocw, H, W, _ptr(off), _ptr(piv))
+    return off, piv[:tot]
+
+
+class Context:
+    """One mimc3cu context (one GPU, one stream)."""
+
+    def __init__(self, device: int = 0):
+        self.L = load_library()
+        h = C.c_void_p()
+        if self.L.mimc3cu_create(device, C.byref(h)):
+            raise Mimc3CuError(self.L.mimc3cu_last_error(None).decode())
+        self.h = h
+        self.device = device
+        self.n = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.mimc3cu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise Mimc3CuError(self.L.mimc3cu_last_error(self.h).decode())
+
+    @property
+    def stream(self) -> int:
+        return self.L.mimc3cu_stream(self.h) or 0
+
+    def sync(self):
+        self._ck(self.L.mimc3cu_sync(self.h))
+
+    def launch_count(self) -> int:
+        return int(self.L.mimc3cu_launch_count(self.h))
+
+    # images ------------------------------------------------------------------------------
+    def image_create(self, H, W) -> int:
+        h = C.c_int32()
+        self._ck(self.L.mimc3cu_image_create(self.h, H, W, C.byref(h)))
+        return h.value
+
+    def image_destroy(self, handle):
+        self._ck(self.L.mimc3cu_image_destroy(self.h, handle))
+
+    def image_upload(self, handle, host):
+        """host: numpy float32 / uint8 / uint16 (H, W)."""
+        host = np.ascontiguousarray(host)
+        fn = {np.dtype(np.float32): self.L.mimc3cu_image_upload, np.dtype(np.uint8): self.L.mimc3cu_image_upload_u8,
+              np.dtype(np.uint16): self.L.mimc3cu_image_upload_u16}[host.dtype]
+        self._ck(fn(self.h, handle, _ptr(host)))
+
+    def image_from(self, arr) -> int:
+        """Create + fill an image from a numpy array (host) or a CUDA torch tensor (device copy)."""
+        H, W = arr.shape
+        h = self.image_create(H, W)
+        if isinstance(arr, np.ndarray):
+            self.image_upload(h, arr)
+        elif arr.is_cuda:
+            import torch
+            assert arr.dtype == torch.float32
+            torch.cuda.current_stream(arr.device).synchronize()
+            self._ck(self.L.mimc3cu_image_copy_from_device(self.h, h, _ptr(arr.contiguous())))
+        else:
+            self.image_upload(h, arr.numpy())
+        return h
+
+    def image_download(self, handle, H, W) -> np.ndarray:
+        out = np.empty((H, W), np.float32)
+        self._ck(self.L.mimc3cu_image_download(self.h, handle, _ptr(out)))
+        return out
+
+    def conv2(self, src, kernel, dst):
+        k = np.ascontiguousarray(kernel, dtype=np.float32)
+        self._ck(self.L.mimc3cu_conv2(self.h, src, _ptr(k), k.shape[0], k.shape[1], dst))
+
+    # nodes / pivots ---------------------------------------------------------------------------
+    def set_nodes(self, xyuvav):
+        x = np.ascontiguousarray(xyuvav, dtype=np.float64)
+        self._ck(self.L.mimc3cu_set_nodes(self.h, _ptr(x), x.shape[0]))
+        self.n = x.shape[0]
+
+    def set_pivots(self, slot, off, piv):
+        off = np.ascontiguousarray(off, dtype=np.int32)
+        piv = np.ascontiguousarray(piv, dtype=np.int32).reshape(-1, 2)
+        if piv.shape[0] == 0:
+            piv = np.zeros((1, 2), np.int32)
+        self._ck(self.L.mimc3cu_set_pivots(self.h, slot, _ptr(off), _ptr(piv), off.shape[0] - 1))
+
+    # matcher -------------------------------------------------------------------------------------
+    def match(self, ref_img, search_img, offset, slot, sign, ocw, negate=False):
+        """Synchronous; returns host arrays dp (n,3), peak (n,2), ncell (n)."""
+        n = self.n
+        dp = np.empty((n, 3), np.float32); peak = np.empty((n, 2), np.int32); ncell = np.empty(n, np.int32)
+        off = np.ascontiguousarray(offset, dtype=np.int32)
+        self._ck(self.L.mimc3cu_match(self.h, ref_img, search_img, _ptr(off), slot, sign, ocw, int(negate),
+                                      _ptr(dp), _ptr(peak), _ptr(ncell)))
+        return dp, peak, ncell
+
+    def match_async(self, ref_img, search_img, offset, slot, sign, ocw, negate, dp_dev, peak_dev=None, ncell_dev=None):
+        off = np.ascontiguousarray(offset, dtype=np.int32)
+        self._ck(self.L.mimc3cu_match_async(self.h, ref_img, search_img, _ptr(off), slot, sign, ocw, int(negate),
+                                            _ptr(dp_dev), _ptr(peak_dev), _ptr(ncell_dev)))
+
+    def find_ncc_peak_batch(self, refchips, sareas, piv):
+        r = np.ascontiguousarray(refchips, dtype=np.float32); s = np.ascontiguousarray(sareas, dtype=np.float32)
+        p = np.ascontiguousarray(piv, dtype=np.int32).reshape(-1, 2)
+        cnt = r.shape[0]
+        uv = np.empty((cnt, 3), np.float32); pk = np.empty((cnt, 2), np.int32); nc = np.empty(cnt, np.int32)
+        self._ck(self.L.mimc3cu_find_ncc_peak_batch(self.h, _ptr(r), r.shape[1], _ptr(s), s.shape[1], cnt, _ptr(p),
+                                                    p.shape[0], _ptr(uv), _ptr(pk), _ptr(nc)))
+        return uv, pk, nc
+
+    def multimatch_async(self, i0, i1, i0c, i1c, offset, params, dp_dev, ncell_dev=None):
+        off = np.ascontiguousarray(offset, dtype=np.int32)
+        self._ck(self.L.mimc3cu_multimatch_async(self.h, i0, i1, i0c, i1c, _ptr(off), C.byref(params), _ptr(dp_dev),
+                                                 _ptr(ncell_dev)))
+
+    # postprocess ------------------------------------------------------------------------------------
+    def cluster_async(self, dp_dev, n, num_dp, mvn_dev, ncl_dev):
+        self._ck(self.L.mimc3cu_cluster_async(self.h, _ptr(dp_dev), n, num_dp, _ptr(mvn_dev), _ptr(ncl_dev)))
+
+    def postprocess(self, dp_dev, xyuvav, params, planes_dev):
+        x = np.ascontiguousarray(xyuvav, dtype=np.float64)
+        stats = np.zeros(4, np.int32)
+        self._ck(self.L.mimc3cu_postprocess(self.h, _ptr(dp_dev), _ptr(x), C.byref(params), _ptr(planes_dev), _ptr(stats)))
+        return stats
+
+    def postprocess_stage(self, which, n):
+        out = np.empty(n, np.float32 if which in (2, 3, 5, 6) else np.int32)
+        self._ck(self.L.mimc3cu_postprocess_stage(self.h, which, _ptr(out)))
+        return out
+
+    def finalize(self, planes_dev, params):
+        a = C.c_float(); b = C.c_float()
+        self._ck(self.L.mimc3cu_finalize(self.h, _ptr(planes_dev), C.byref(params), C.byref(a), C.byref(b)))
+        return a.value, b.value

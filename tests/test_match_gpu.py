@@ -1,0 +1,120 @@
+"""GPU parity of the DLC-NCC matcher (through the C ABI) against the oracle.
+
+Bar (BASELINE.json north_star): integer peaks and valid/null flags bit-exact, sub-pixel
+displacements within 0.01 px, NCC within 1e-5 relative.  The CUDA path is built to be
+bit-identical in all three, so the tests assert bit equality (NaN-aware) and would also
+report the tolerance-level numbers on failure.
+"""
+import numpy as np
+import pytest
+
+from mimc3_b200 import lib, synth
+from tests.util import VEC_OCW, mismatch_report, same_bits_nan_aware, small_scene
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_both(gpu_ctx, orc, sc, a, b, offset, sign, ocw, slot=0):
+    H, W = a.shape
+    p = lib.params_for(sc.xyuvav, sc.dimx, sc.dimy, sc.dt)
+    off, piv = lib.get_uv_pivot(sc.xyuvav, sc.dt, p.mpp, ocw, H, W)
+    off_o, piv_o = orc.get_uv_pivot(sc.xyuvav, sc.dt, p.mpp, ocw, H, W)
+    assert np.array_equal(off, off_o) and np.array_equal(piv, piv_o)
+    gpu_ctx.set_nodes(sc.xyuvav)
+    gpu_ctx.set_pivots(slot, off, piv)
+    ia, ib = gpu_ctx.image_from(a), gpu_ctx.image_from(b)
+    try:
+        dp, peak, ncell = gpu_ctx.match(ia, ib, offset, slot, sign, ocw)
+    finally:
+        gpu_ctx.image_destroy(ia); gpu_ctx.image_destroy(ib)
+    dpo, peako, ncello = orc.match(a, b, sc.xyuvav, offset, off, piv, sign, ocw)
+    return (dp, peak, ncell), (dpo, peako, ncello)
+
+
+def _assert_parity(got, want, tag):
+    (dp, peak, ncell), (dpo, peako, ncello) = got, want
+    assert np.array_equal(dpo[:, 2] == -3, dp[:, 2] == -3), tag + " validity flags differ"
+    assert np.array_equal(peak, peako), tag + " integer peaks differ: " + mismatch_report(peak, peako)
+    assert np.array_equal(ncell, ncello), tag + " evaluated-cell counts differ"
+    fin = np.isfinite(dpo[:, 0]) & np.isfinite(dpo[:, 1])
+    assert np.array_equal(fin, np.isfinite(dp[:, 0]) & np.isfinite(dp[:, 1]))
+    assert np.max(np.abs(dp[fin, :2] - dpo[fin, :2]), initial=0) <= 0.01, tag       # sub-pixel tolerance
+    assert np.allclose(dp[:, 2], dpo[:, 2], rtol=1e-5, atol=0), tag                 # NCC tolerance
+    assert same_bits_nan_aware(dp, dpo), tag + " not bit-identical: " + mismatch_report(dp, dpo)
+
+
+@pytest.mark.parametrize("ocw", VEC_OCW)
+@pytest.mark.parametrize("direction", ["fwd", "swapped"])
+def test_match_u8_with_null_wedge(gpu_ctx, orc, ocw, direction):
+    sc = small_scene()
+    i0, i1 = sc.i0.numpy(), sc.i1.numpy()
+    offset = np.array(sc.offset, np.int32)
+    if direction == "fwd":
+        got, want = _run_both(gpu_ctx, orc, sc, i0, i1, offset, +1, ocw)
+    else:
+        got, want = _run_both(gpu_ctx, orc, sc, i1, i0, -offset, -1, ocw)
+    _assert_parity(got, want, f"u8 ocw={ocw} {direction}")
+    assert (want[0][:, 2] == -3).sum() > 0 or ocw >= 30      # the wedge invalidates some small-chip nodes
+
+
+@pytest.mark.parametrize("ocw", (15, 40))
+def test_match_u16(gpu_ctx, orc, ocw):
+    """uint16-range data: float products exceed 2^24 and are rounded like the reference's."""
+    sc = small_scene(dtype="u16", seed=9, null_wedge=False)
+    i0, i1 = sc.i0.numpy(), sc.i1.numpy()
+    i0 = np.minimum(i0 * 3.9, 65535).round().astype(np.float32)    # reach DN > 60000
+    i1 = np.minimum(i1 * 3.9, 65535).round().astype(np.float32)
+    assert i0.max() > 60000
+    got, want = _run_both(gpu_ctx, orc, sc, i0, i1, np.array(sc.offset, np.int32), +1, ocw)
+    _assert_parity(got, want, f"u16 ocw={ocw}")
+
+
+@pytest.mark.parametrize("kid", (0, 1, 2))
+def test_match_on_filtered_images(gpu_ctx, orc, kid):
+    """conv2-filtered inputs (multiples of 1/8 for the Laplacian), CPU-filtered so that only
+    the matcher is under test."""
+    import oracle
+    sc = small_scene(seed=21)
+    i0, i1 = sc.i0.numpy(), sc.i1.numpy()
+    c0 = np.zeros_like(i0); c1 = np.zeros_like(i1)
+    orc.conv2(i0, kid, c0); orc.conv2(i1, kid, c1)
+    got, want = _run_both(gpu_ctx, orc, sc, c0, c1, np.array(sc.offset, np.int32), +1, 15)
+    _assert_parity(got, want, f"filtered kernel {kid}")
+
+
+def test_match_fast_glacier_wide_windows(gpu_ctx, orc):
+    """Config-4-like: ~40 px a-priori displacement => ~80 pivots and search areas that do not
+    fit the small-window fast sizes."""
+    sc = small_scene(H=900, W=900, seed=33, peak_px=43.0, apriori_gain=0.9, spacing=41, null_wedge=False,
+                     band_width_frac=0.2)
+    i0, i1 = sc.i0.numpy(), sc.i1.numpy()
+    got, want = _run_both(gpu_ctx, orc, sc, i0, i1, np.array(sc.offset, np.int32), +1, 40)
+    assert want[2].max() > 200     # many evaluated cells
+    _assert_parity(got, want, "fast glacier ocw=40")
+
+
+def test_match_nodes_at_image_border(gpu_ctx, orc):
+    """Search areas hanging over the image edge are zero-filled (extract_sarea boundary check)."""
+    sc = small_scene(H=400, W=400, seed=41, null_wedge=False, margin=44, spacing=39, peak_px=9.0)
+    i0, i1 = sc.i0.numpy(), sc.i1.numpy()
+    got, want = _run_both(gpu_ctx, orc, sc, i0, i1, np.array((7, -6), np.int32), +1, 40)
+    _assert_parity(got, want, "border nodes")
+
+
+def test_find_ncc_peak_batch_cp_shape(gpu_ctx, orc):
+    """The CP stage's call shape: 85x85 search chips, 61x61 / 31x31 reference chips, 21x21
+    rectangular pivot set (MIMC_module.c:165-176, 351)."""
+    sc = small_scene(seed=55, null_wedge=False)
+    i0, i1 = sc.i0.numpy(), sc.i1.numpy()
+    piv = np.array([(a, b) for a in range(-10, 11) for b in range(-10, 11)], np.int32)
+    rng = np.random.default_rng(3)
+    cs = rng.integers(100, 540, size=(6, 2))
+    for ocw in (15, 30):
+        S = 2 * ocw + 1
+        chips = np.stack([i0[v - ocw:v + ocw + 1, u - ocw:u + ocw + 1] for u, v in cs])
+        sas = np.stack([i1[v - 42:v + 43, u - 42:u + 43] for u, v in cs])
+        uv, pk, nc = gpu_ctx.find_ncc_peak_batch(chips, sas, piv)
+        for k in range(len(cs)):
+            uvo, pko, nco = orc.find_ncc_peak(chips[k], sas[k], piv)
+            assert np.array_equal(pk[k], pko) and nc[k] == nco
+            assert same_bits_nan_aware(uv[k], uvo), (ocw, k, uv[k], uvo)
