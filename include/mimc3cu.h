@@ -158,6 +158,17 @@ int mimc3cu_postprocess_stage(mimc3cu_ctx *ctx, int32_t which, void *host);
  * float sums), px -> m/yr, vy sign flip, sqrt of the variances. In place on planes_dev. */
 int mimc3cu_finalize(mimc3cu_ctx *ctx, float *planes_dev, const mimc3cu_params *p, float *du_cp, float *dv_cp);
 
+/* ---- measurement helper --------------------------------------------------------------- */
+/* Sustained FP32 FMA throughput of this GPU's CUDA cores (TFLOP/s, best of 4 timed
+ * launches of a register-resident FMA chain): the matcher's roofline denominator. */
+int mimc3cu_fp32_peak(mimc3cu_ctx *ctx, double *tflops, double *ms);
+
+/* Per-kernel-family CUDA-event timing on the context stream: family 0 = matcher kernel,
+ * 1 = conv2, 2 = postprocess (whole call). timing_read synchronises, returns the summed
+ * milliseconds and launch counts since the last read, and clears the timers. */
+int mimc3cu_timing_enable(mimc3cu_ctx *ctx, int on);
+int mimc3cu_timing_read(mimc3cu_ctx *ctx, double *ms3, int64_t *counts3);
+
 /* ---- device memory helpers (so a plain-C host needs no CUDA headers) -------------- */
 int mimc3cu_malloc(mimc3cu_ctx *ctx, size_t bytes, void **dev);
 int mimc3cu_free(mimc3cu_ctx *ctx, void *dev);

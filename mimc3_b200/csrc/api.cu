@@ -34,6 +34,24 @@ int ensure_scratch(mimc3cu_ctx *ctx, size_t bytes) {
     return 0;
 }
 
+static cudaEvent_t take_event(mimc3cu_ctx *ctx) {
+    cudaEvent_t e = nullptr;
+    if (!ctx->event_pool.empty()) { e = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+}
+
+ScopedTimer::ScopedTimer(mimc3cu_ctx *c, int fam) : ctx(c), family(fam) {
+    if (!ctx->timing) return;
+    cudaEvent_t start = take_event(ctx);
+    stop = take_event(ctx);
+    cudaEventRecord(start, ctx->stream);
+    ctx->timers[family].push_back({start, stop});
+}
+ScopedTimer::~ScopedTimer() {
+    if (stop) cudaEventRecord(stop, ctx->stream);
+}
+
 Image *get_image(mimc3cu_ctx *ctx, int32_t h) {
     if (!ctx || h < 0 || h >= (int32_t)ctx->images.size() || !ctx->images[h].used) return nullptr;
     return &ctx->images[h];
@@ -232,6 +250,7 @@ int mimc3cu_conv2(mimc3cu_ctx *ctx, int32_t src, const float *kernel, int32_t kh
     if (!s || !d) return mimc3cu_fail(ctx, "conv2: bad image handle");
     if (s == d) return mimc3cu_fail(ctx, "conv2: src and dst must differ");
     if (s->H != d->H || s->W != d->W) return mimc3cu_fail(ctx, "conv2: size mismatch");
+    ScopedTimer tm(ctx, 1);
     return launch_conv2(ctx, s->d, s->H, s->W, kernel, kh, kw, d->d);
 }
 
@@ -334,6 +353,7 @@ int mimc3cu_match_async(mimc3cu_ctx *ctx, int32_t ref_img, int32_t search_img, c
     L.dp = dp_dev; L.peak = peak_dev; L.ncell = ncell_dev;
     L.max_cells = ps.max_cells;
     L.max_sarea = (int64_t)(2 * (ps.max_abs_u + ocw + 2) + 1) * (2 * (ps.max_abs_v + ocw + 2) + 1);
+    ScopedTimer tm(ctx, 0);
     return launch_match(ctx, L);
 }
 
@@ -439,11 +459,32 @@ int mimc3cu_cluster_async(mimc3cu_ctx *ctx, const float *dp_dev, int32_t n, int3
 }
 int mimc3cu_postprocess(mimc3cu_ctx *ctx, const float *dp_dev, const double *xyuvav, const mimc3cu_params *p,
                         float *planes_dev, int32_t *stats) {
+    ScopedTimer tm(ctx, 2);
     return post_run(ctx, dp_dev, xyuvav, p, planes_dev, stats);
 }
 int mimc3cu_postprocess_stage(mimc3cu_ctx *ctx, int32_t which, void *host) { return post_stage(ctx, which, host); }
 int mimc3cu_finalize(mimc3cu_ctx *ctx, float *planes_dev, const mimc3cu_params *p, float *du_cp, float *dv_cp) {
     return post_finalize(ctx, planes_dev, p, du_cp, dv_cp);
+}
+
+/* ---- timing ---------------------------------------------------------------------------------- */
+int mimc3cu_timing_enable(mimc3cu_ctx *ctx, int on) { ctx->timing = on != 0; return 0; }
+
+int mimc3cu_timing_read(mimc3cu_ctx *ctx, double *ms, int64_t *counts) {
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int f = 0; f < 3; f++) {
+        double tot = 0.0;
+        for (auto &pr : ctx->timers[f]) {
+            float t = 0.f;
+            CU_CHECK(ctx, cudaEventElapsedTime(&t, pr.first, pr.second));
+            tot += t;
+            ctx->event_pool.push_back(pr.first); ctx->event_pool.push_back(pr.second);
+        }
+        if (ms) ms[f] = tot;
+        if (counts) counts[f] = (int64_t)ctx->timers[f].size();
+        ctx->timers[f].clear();
+    }
+    return 0;
 }
 
 /* ---- memory helpers ------------------------------------------------------------------------ */

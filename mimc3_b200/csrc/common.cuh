@@ -52,6 +52,20 @@ struct mimc3cu_ctx {
 
     // postprocess state kept for mimc3cu_postprocess_stage
     struct Post *post = nullptr;
+
+    // optional per-kernel-family event timing (0 match, 1 conv2/ingest, 2 postprocess)
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timers[3];
+    std::vector<cudaEvent_t> event_pool;
+};
+
+// RAII event bracket: records start now and stop at scope exit when ctx->timing is on.
+struct ScopedTimer {
+    mimc3cu_ctx *ctx;
+    int family;
+    cudaEvent_t stop = nullptr;
+    ScopedTimer(mimc3cu_ctx *c, int fam);
+    ~ScopedTimer();
 };
 
 extern std::string g_mimc3cu_error;

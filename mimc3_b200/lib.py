@@ -70,6 +70,9 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "mimc3cu_postprocess": (C.c_int, [vp, vp, vp, C.POINTER(Params), vp, vp]),
         "mimc3cu_postprocess_stage": (C.c_int, [vp, i32, vp]),
         "mimc3cu_finalize": (C.c_int, [vp, vp, C.POINTER(Params), C.POINTER(f32), C.POINTER(f32)]),
+        "mimc3cu_fp32_peak": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+        "mimc3cu_timing_enable": (C.c_int, [vp, C.c_int]),
+        "mimc3cu_timing_read": (C.c_int, [vp, vp, vp]),
         "mimc3cu_malloc": (C.c_int, [vp, C.c_size_t, C.POINTER(vp)]),
         "mimc3cu_free": (C.c_int, [vp, vp]),
         "mimc3cu_memcpy_d2h": (C.c_int, [vp, vp, vp, C.c_size_t]),
@@ -91,7 +94,8 @@ EXPORTED_SYMBOLS = (
     "mimc3cu_image_copy_from_device", "mimc3cu_image_download", "mimc3cu_image_ptr", "mimc3cu_conv2",
     "mimc3cu_get_uv_pivot", "mimc3cu_set_nodes", "mimc3cu_set_pivots", "mimc3cu_match_async", "mimc3cu_match",
     "mimc3cu_find_ncc_peak_batch", "mimc3cu_multimatch_async", "mimc3cu_cluster_async", "mimc3cu_postprocess",
-    "mimc3cu_postprocess_stage", "mimc3cu_finalize", "mimc3cu_malloc", "mimc3cu_free", "mimc3cu_memcpy_d2h",
+    "mimc3cu_postprocess_stage", "mimc3cu_finalize", "mimc3cu_fp32_peak", "mimc3cu_timing_enable",
+    "mimc3cu_timing_read", "mimc3cu_malloc", "mimc3cu_free", "mimc3cu_memcpy_d2h",
     "mimc3cu_memcpy_h2d",
 )
 
@@ -274,6 +278,21 @@ class Context:
         out = np.empty(n, np.float32 if which in (2, 3, 5, 6) else np.int32)
         self._ck(self.L.mimc3cu_postprocess_stage(self.h, which, _ptr(out)))
         return out
+
+    def fp32_peak(self):
+        """(TFLOP/s, ms) of the FMA micro-benchmark."""
+        a = C.c_double(); b = C.c_double()
+        self._ck(self.L.mimc3cu_fp32_peak(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def timing_enable(self, on=True):
+        self._ck(self.L.mimc3cu_timing_enable(self.h, int(on)))
+
+    def timing_read(self):
+        """(ms[3], counts[3]) for the families match / conv2 / postprocess since the last read."""
+        ms = np.zeros(3, np.float64); cnt = np.zeros(3, np.int64)
+        self._ck(self.L.mimc3cu_timing_read(self.h, _ptr(ms), _ptr(cnt)))
+        return ms, cnt
 
     def finalize(self, planes_dev, params):
         a = C.c_float(); b = C.c_float()

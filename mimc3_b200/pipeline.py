@@ -1,0 +1,87 @@
+"""Host-side mirror of the reference driver's flow over the C ABI (MIMC_main.c:229-402):
+load the pair -> (CP offset) -> pivots -> 32-attempt multi-match -> postprocess -> finalize.
+
+PyTorch is used for device memory only; all compute goes through libmimc3cu.so.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import lib
+
+VEC_OCW = (7, 15, 30, 40)   # MIMC_main.c:134-137
+
+
+class Pipeline:
+    def __init__(self, device: int = 0):
+        self.ctx = lib.Context(device)
+        self.device = torch.device("cuda", device)
+        self.stream = torch.cuda.ExternalStream(self.ctx.stream, device=self.device)
+        self.handles = {}
+        self.n = 0
+        self.params = None
+        self.H = self.W = 0
+
+    def close(self):
+        self.ctx.close()
+
+    # ---- inputs ---------------------------------------------------------------------------
+    def _ensure_images(self, H, W):
+        if (H, W) != (self.H, self.W):
+            for h in self.handles.values():
+                self.ctx.image_destroy(h)
+            self.handles = {k: self.ctx.image_create(H, W) for k in ("i0", "i1", "i0c", "i1c")}
+            self.H, self.W = H, W
+
+    def set_images(self, i0, i1):
+        """i0/i1: numpy (float32 / uint8 / uint16, host) or CUDA float32 torch tensors."""
+        H, W = i0.shape
+        self._ensure_images(H, W)
+        for key, img in (("i0", i0), ("i1", i1)):
+            if isinstance(img, np.ndarray):
+                self.ctx.image_upload(self.handles[key], img)
+            elif img.is_cuda:
+                torch.cuda.current_stream(img.device).synchronize()
+                self.ctx._ck(self.ctx.L.mimc3cu_image_copy_from_device(self.ctx.h, self.handles[key], img.contiguous().data_ptr()))
+            else:
+                self.ctx.image_upload(self.handles[key], img.numpy())
+
+    def set_grid(self, xyuvav, dimx, dimy, dt):
+        """Nodes + the four pivot sets (get_uv_pivot per chip size, MIMC_main.c:264)."""
+        x = np.ascontiguousarray(xyuvav, dtype=np.float64)
+        self.params = lib.params_for(x, dimx, dimy, dt)
+        self.xyuvav = x
+        self.n = x.shape[0]
+        self.ctx.set_nodes(x)
+        self.pivot_bytes = 0
+        for slot, ocw in enumerate(VEC_OCW):
+            off, piv = lib.get_uv_pivot(x, dt, self.params.mpp, ocw, self.H, self.W, self.params.AW_SF, self.params.AW_CRE)
+            self.ctx.set_pivots(slot, off, piv)
+            self.pivot_bytes += off.nbytes + piv.nbytes
+
+    # ---- compute --------------------------------------------------------------------------------
+    def multimatch(self, offset, want_ncell=False):
+        """All 32 attempts (MIMC_main.c:261-350) -> dp (32, n, 3) on the device."""
+        dp = torch.empty((32, self.n, 3), dtype=torch.float32, device=self.device)
+        ncell = torch.empty((32, self.n), dtype=torch.int32, device=self.device) if want_ncell else None
+        h = self.handles
+        self.ctx.multimatch_async(h["i0"], h["i1"], h["i0c"], h["i1c"], offset, self.params, dp, ncell)
+        return dp, ncell
+
+    def postprocess(self, dp):
+        planes = torch.empty((5, self.params.dimy, self.params.dimx), dtype=torch.float32, device=self.device)
+        stats = self.ctx.postprocess(dp, self.xyuvav, self.params, planes)
+        return planes, stats
+
+    def run(self, i0, i1, xyuvav, dimx, dimy, dt, offset, finalize=True):
+        """End to end from host buffers to the five host planes (+ CP sub-pixel bias)."""
+        self.set_images(i0, i1)
+        self.set_grid(xyuvav, dimx, dimy, dt)
+        dp, _ = self.multimatch(offset)
+        planes, stats = self.postprocess(dp)
+        bias = (0.0, 0.0)
+        if finalize:
+            bias = self.ctx.finalize(planes, self.params)
+        self.ctx.sync()
+        return planes.cpu().numpy(), stats, bias

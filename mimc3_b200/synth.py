@@ -77,10 +77,11 @@ def _blur(img: torch.Tensor, sigma: float) -> torch.Tensor:
 
 def make_texture(H: int, W: int, seed: int, device="cpu") -> torch.Tensor:
     """Unit-range texture in [0, 1], (H, W) float32."""
-    g = torch.Generator(device="cpu").manual_seed(seed)
-    out = torch.zeros(H, W, dtype=torch.float32, device=device)
+    dev = torch.device(device)
+    g = torch.Generator(device=dev).manual_seed(seed)   # the stream depends on the device type
+    out = torch.zeros(H, W, dtype=torch.float32, device=dev)
     for sigma, wgt in ((1.5, 1.0), (5.0, 0.7), (15.0, 0.5)):
-        noise = torch.randn(H, W, generator=g, dtype=torch.float32).to(device)
+        noise = torch.randn(H, W, generator=g, dtype=torch.float32, device=dev)
         b = _blur(noise, sigma)
         b = (b - b.mean()) / b.std()
         out += wgt * b
@@ -143,13 +144,13 @@ def make_scene(
     del sx, sy
     i1 = F.grid_sample(i0[None, None], grid, mode="bicubic", padding_mode="reflection", align_corners=False)[0, 0]
     del grid
-    g = torch.Generator(device="cpu").manual_seed(seed + 1)
+    g = torch.Generator(device=dev).manual_seed(seed + 1)
     if noise_dn > 0:
-        # noise generated in row blocks to bound host memory on the big configs
+        # noise generated in row blocks to bound memory on the big configs
         blk = 2048
         for r0 in range(0, H, blk):
             r1 = min(H, r0 + blk)
-            i1[r0:r1] += noise_dn * torch.randn(r1 - r0, W, generator=g, dtype=torch.float32).to(dev)
+            i1[r0:r1] += noise_dn * torch.randn(r1 - r0, W, generator=g, dtype=torch.float32, device=dev)
     i1 = torch.clamp(torch.round(i1), lo, hi if dtype == "u8" else 65535.0)
 
     rng = np.random.default_rng(seed + 2)
@@ -168,8 +169,9 @@ def make_scene(
         us, vs = us[: max_nodes_xy[0]], vs[: max_nodes_xy[1]]
     dimx, dimy = len(us), len(vs)
     uu, vv = np.meshgrid(us, vs)  # (dimy, dimx), u fastest
-    du_n = du.cpu()[torch.from_numpy(vv), torch.from_numpy(uu)].numpy().astype(np.float64)
-    dv_n = dv.cpu()[torch.from_numpy(vv), torch.from_numpy(uu)].numpy().astype(np.float64)
+    vi, ui = torch.from_numpy(vv).to(dev), torch.from_numpy(uu).to(dev)
+    du_n = du[vi, ui].cpu().numpy().astype(np.float64)
+    dv_n = dv[vi, ui].cpu().numpy().astype(np.float64)
     del du, dv
 
     if null_wedge:
