@@ -121,6 +121,18 @@ int mimc3cu_match(mimc3cu_ctx *ctx, int32_t ref_img, int32_t search_img, const i
                   int32_t pivot_slot, int32_t sign, int32_t ocw, int32_t negate_duv,
                   float *dp_host, int32_t *peak_host, int32_t *ncell_host);
 
+/* Matcher selection.  The library has two CUDA implementations of the cell evaluator with
+ * identical results: the general FP64-accumulating kernel (any float image) and the exact-FP32
+ * kernel (images whose pixels are non-negative multiples of 1/8, i.e. everything
+ * GMA_float_load_tiff and GMA_float_conv2 produce; it uses per-image summed-area tables).
+ * mode 0 = automatic per call (default; env MIMC3CU_MATCHER=v1|v2 overrides at context creation),
+ * 1 = always the general kernel, 2 = require the exact-FP32 kernel (calls outside its class fail). */
+int mimc3cu_set_matcher(mimc3cu_ctx *ctx, int32_t mode);
+/* 1 / 2: which of the two the last mimc3cu_match* call used (0: none yet). */
+int mimc3cu_last_matcher(const mimc3cu_ctx *ctx);
+/* Image class as seen by the matcher: exact_class (0/1), fractional bits (0 or 3), maximum. */
+int mimc3cu_image_class(mimc3cu_ctx *ctx, int32_t handle, int32_t *exact_class, int32_t *frac_bits, float *max_value);
+
 /* find_ncc_peak on explicit chips (the CP stage's call shape, MIMC_module.c:351,369):
  * `count` independent problems; refchips (count, S, S), sareas (count, D, D) float32 on
  * the HOST, one shared pivot list (P,2).  Results to host: uvncc (count,3), peak (count,2). */

@@ -152,6 +152,11 @@ int mimc3cu_create(int device, mimc3cu_ctx **out) {
     CU_CHECK(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CU_CHECK(nullptr, cudaMalloc(&ctx->counter, 256));
     CU_CHECK(nullptr, cudaMalloc(&ctx->minbuf, 4096 * sizeof(float)));
+    CU_CHECK(nullptr, cudaMalloc(&ctx->statbuf, 64));
+    if (const char *m = getenv("MIMC3CU_MATCHER")) {
+        if (!strcmp(m, "v1") || !strcmp(m, "general")) ctx->matcher = 1;
+        else if (!strcmp(m, "v2")) ctx->matcher = 2;
+    }
     *out = ctx;
     return 0;
 }
@@ -161,8 +166,14 @@ void mimc3cu_destroy(mimc3cu_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     post_free(ctx);
-    for (auto &im : ctx->images) if (im.used && im.d) cudaFree(im.d);
-    for (auto &p : ctx->pivots) { if (p.off) cudaFree(p.off); if (p.piv) cudaFree(p.piv); }
+    for (auto &im : ctx->images) if (im.used) { if (im.d) cudaFree(im.d); if (im.sat) cudaFree(im.sat); }
+    for (auto &p : ctx->pivots) {
+        if (p.off) cudaFree(p.off);
+        if (p.piv) cudaFree(p.piv);
+        for (auto &b : p.bins) if (b.lists) cudaFree(b.lists);
+    }
+    if (ctx->statbuf) cudaFree(ctx->statbuf);
+    if (ctx->overflow_list) cudaFree(ctx->overflow_list);
     if (ctx->node_uv) cudaFree(ctx->node_uv);
     if (ctx->xyuvav_d) cudaFree(ctx->xyuvav_d);
     if (ctx->scratch) cudaFree(ctx->scratch);
@@ -197,6 +208,7 @@ int mimc3cu_image_destroy(mimc3cu_ctx *ctx, int32_t handle) {
     if (!im) return mimc3cu_fail(ctx, "image_destroy: bad handle %d", handle);
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     CU_CHECK(ctx, cudaFree(im->d));
+    if (im->sat) CU_CHECK(ctx, cudaFree(im->sat));
     *im = Image();
     return 0;
 }
@@ -204,6 +216,7 @@ int mimc3cu_image_destroy(mimc3cu_ctx *ctx, int32_t handle) {
 int mimc3cu_image_upload(mimc3cu_ctx *ctx, int32_t handle, const float *host) {
     Image *im = get_image(ctx, handle);
     if (!im) return mimc3cu_fail(ctx, "image_upload: bad handle %d", handle);
+    image_invalidate(im);
     CU_CHECK(ctx, cudaMemcpyAsync(im->d, host, (size_t)im->H * im->W * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -213,6 +226,7 @@ static int upload_int(mimc3cu_ctx *ctx, int32_t handle, const void *host, int by
     Image *im = get_image(ctx, handle);
     if (!im) return mimc3cu_fail(ctx, "image_upload: bad handle %d", handle);
     size_t count = (size_t)im->H * im->W;
+    image_invalidate(im);
     if (int rc = ensure_scratch(ctx, count * bytes_per_px)) return rc;
     CU_CHECK(ctx, cudaMemcpyAsync(ctx->scratch, host, count * bytes_per_px, cudaMemcpyHostToDevice, ctx->stream));
     int rc = bytes_per_px == 1 ? launch_cast_u8(ctx, (const uint8_t *)ctx->scratch, im->d, count)
@@ -227,6 +241,7 @@ int mimc3cu_image_upload_u16(mimc3cu_ctx *ctx, int32_t handle, const uint16_t *h
 int mimc3cu_image_copy_from_device(mimc3cu_ctx *ctx, int32_t handle, const float *dev) {
     Image *im = get_image(ctx, handle);
     if (!im) return mimc3cu_fail(ctx, "image_copy_from_device: bad handle %d", handle);
+    image_invalidate(im);
     CU_CHECK(ctx, cudaMemcpyAsync(im->d, dev, (size_t)im->H * im->W * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
@@ -251,6 +266,7 @@ int mimc3cu_conv2(mimc3cu_ctx *ctx, int32_t src, const float *kernel, int32_t kh
     if (s == d) return mimc3cu_fail(ctx, "conv2: src and dst must differ");
     if (s->H != d->H || s->W != d->W) return mimc3cu_fail(ctx, "conv2: size mismatch");
     ScopedTimer tm(ctx, 1);
+    image_invalidate(d);
     return launch_conv2(ctx, s->d, s->H, s->W, kernel, kh, kw, d->d);
 }
 
@@ -310,6 +326,7 @@ int mimc3cu_set_pivots(mimc3cu_ctx *ctx, int32_t slot, const int32_t *off, const
     CU_CHECK(ctx, cudaSetDevice(ctx->device));
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     PivotSet &ps = ctx->pivots[slot];
+    for (auto &b : ps.bins) { if (b.lists) { CU_CHECK(ctx, cudaFree(b.lists)); b.lists = nullptr; } b.ocw = -1; }
     if (ps.off) { CU_CHECK(ctx, cudaFree(ps.off)); ps.off = nullptr; }
     if (ps.piv) { CU_CHECK(ctx, cudaFree(ps.piv)); ps.piv = nullptr; }
     ps.n = n; ps.total = off[n];
@@ -340,7 +357,7 @@ int mimc3cu_match_async(mimc3cu_ctx *ctx, int32_t ref_img, int32_t search_img, c
     if (r->H != s->H || r->W != s->W) return mimc3cu_fail(ctx, "match: the two images must have the same size");
     if (pivot_slot < 0 || pivot_slot >= MIMC3CU_MAX_PIVOT_SLOTS || !ctx->pivots[pivot_slot].off)
         return mimc3cu_fail(ctx, "match: pivot slot %d is empty", pivot_slot);
-    const PivotSet &ps = ctx->pivots[pivot_slot];
+    PivotSet &ps = ctx->pivots[pivot_slot];
     if (!ctx->node_uv || ps.n != ctx->n) return mimc3cu_fail(ctx, "match: nodes not set or pivot/node count mismatch");
     if (!dp_dev) return mimc3cu_fail(ctx, "match: dp output is required");
     if (sign != 1 && sign != -1) return mimc3cu_fail(ctx, "match: sign must be +1 or -1");
@@ -353,8 +370,38 @@ int mimc3cu_match_async(mimc3cu_ctx *ctx, int32_t ref_img, int32_t search_img, c
     L.dp = dp_dev; L.peak = peak_dev; L.ncell = ncell_dev;
     L.max_cells = ps.max_cells;
     L.max_sarea = (int64_t)(2 * (ps.max_abs_u + ocw + 2) + 1) * (2 * (ps.max_abs_v + ocw + 2) + 1);
+    bool v2 = false;
+    if (ctx->matcher != 1) {
+        {   // image statistics + summed-area tables (cached until the image changes): preprocessing family
+            ScopedTimer tp(ctx, 1);
+            if (int rc = ensure_image_sat(ctx, r)) return rc;
+            if (int rc = ensure_image_sat(ctx, s)) return rc;
+        }
+        v2 = match2_supported(L, r, s);
+        if (!v2 && ctx->matcher == 2)
+            return mimc3cu_fail(ctx, "match: the exact-FP32 matcher was required (MIMC3CU_MATCHER=v2) but this image pair / "
+                                     "chip size is outside its class");
+    }
+    ctx->last_matcher = v2 ? 2 : 1;
     ScopedTimer tm(ctx, 0);
-    return launch_match(ctx, L);
+    return v2 ? launch_match2(ctx, L, r, s, &ps) : launch_match(ctx, L);
+}
+
+int mimc3cu_set_matcher(mimc3cu_ctx *ctx, int32_t mode) {
+    if (mode < 0 || mode > 2) return mimc3cu_fail(ctx, "set_matcher: mode must be 0 (auto), 1 (general FP64) or 2 (require exact-FP32)");
+    ctx->matcher = mode;
+    return 0;
+}
+int mimc3cu_last_matcher(const mimc3cu_ctx *ctx) { return ctx->last_matcher; }
+
+int mimc3cu_image_class(mimc3cu_ctx *ctx, int32_t handle, int32_t *exact_class, int32_t *frac_bits, float *max_value) {
+    Image *im = get_image(ctx, handle);
+    if (!im) return mimc3cu_fail(ctx, "image_class: bad handle %d", handle);
+    if (int rc = ensure_image_stats(ctx, im)) return rc;
+    if (exact_class) *exact_class = im->exact_class ? 1 : 0;
+    if (frac_bits) *frac_bits = im->frac_bits;
+    if (max_value) *max_value = im->max_value;
+    return 0;
 }
 
 int mimc3cu_match(mimc3cu_ctx *ctx, int32_t ref_img, int32_t search_img, const int32_t *offset, int32_t pivot_slot,

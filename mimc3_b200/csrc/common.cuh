@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -14,6 +16,12 @@ struct Image {
     float *d = nullptr;
     int32_t H = 0, W = 0;
     bool used = false;
+    // sat.cu: statistics + summed-area table, valid until the payload changes
+    bool stats_valid = false, sat_valid = false;
+    bool exact_class = false;     // finite, >= 0, multiples of 2^-frac_bits, scaled max < 2^24
+    float max_value = 0.0f;
+    int frac_bits = 0;            // 0 (integer DN) or 3 (multiples of 1/8)
+    void *sat = nullptr;          // ulonglong2[(H+1)*(W+1)]
 };
 
 struct PivotSet {
@@ -25,6 +33,14 @@ struct PivotSet {
     int64_t max_cells = 0;                  // max (2|ul|+4)(2|vl|+4): reachable cmap region
     int64_t max_sarea_extra = 0;            // helper: max over nodes of (|ul|+2, |vl|+2) product terms
     std::vector<int32_t> last_u, last_v;    // host copy of |last pivot| per node (for smem sizing)
+    // match2.cu: node lists per shared-memory bin, cached per chip half-width
+    struct Bins {
+        int32_t ocw = -1;
+        int32_t *lists = nullptr;            // device: concatenated node indices
+        int32_t count[4] = {0, 0, 0, 0};     // [0..2] v2 bins (3/2/1 CTAs per SM), [3] general kernel
+        int32_t start[4] = {0, 0, 0, 0};
+        int64_t sa_cap[3] = {0, 0, 0}, cell_cap[3] = {0, 0, 0};
+    } bins[2];
 };
 
 struct mimc3cu_ctx {
@@ -49,6 +65,11 @@ struct mimc3cu_ctx {
     size_t scratch_bytes = 0;
     unsigned int *counter = nullptr;   // dynamic node fetch
     float *minbuf = nullptr;           // conv2 reduction
+    unsigned int *statbuf = nullptr;   // image statistics (sat.cu)
+    int *overflow_list = nullptr;      // nodes the v2 matcher hands to the general kernel
+    size_t overflow_cap = 0;
+    int matcher = 0;                   // 0 auto, 1 force the general FP64 kernel, 2 require v2
+    int last_matcher = 0;              // which kernel family the last match call used (1 general, 2 exact-FP32)
 
     // postprocess state kept for mimc3cu_postprocess_stage
     struct Post *post = nullptr;
@@ -103,8 +124,20 @@ struct MatchLaunch {
     int32_t *peak = nullptr, *ncell = nullptr;
     int64_t max_cells = 0;       // reachable cmap cells, max over nodes
     int64_t max_sarea = 0;       // Dx2*Dy2, max over nodes
+    // optional indirection: process node_list[0 .. *list_count) instead of 0..n-1
+    const int32_t *node_list = nullptr;
+    const unsigned int *list_count = nullptr;   // device; NULL => list_n
+    int32_t list_n = 0;
 };
 int launch_match(mimc3cu_ctx *ctx, const MatchLaunch &L);
+// match2.cu: exact-FP32 matcher for exact-class image pairs; falls back to launch_match per node
+int launch_match2(mimc3cu_ctx *ctx, const MatchLaunch &L, const Image *ref, const Image *srch, PivotSet *ps);
+bool match2_supported(const MatchLaunch &L, const Image *ref, const Image *srch);
+
+// sat.cu
+void image_invalidate(Image *im);
+int ensure_image_stats(mimc3cu_ctx *ctx, Image *im);
+int ensure_image_sat(mimc3cu_ctx *ctx, Image *im);
 
 // conv2.cu
 int launch_conv2(mimc3cu_ctx *ctx, const float *src, int32_t H, int32_t W, const float *kernel, int32_t kh,

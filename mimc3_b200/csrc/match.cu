@@ -44,6 +44,9 @@ struct MatchArgs {
     unsigned char *scr_flag;
     long long scr_stride;
     unsigned int *counter;
+    const int *node_list;            // optional indirection (NULL: nodes 0..n-1)
+    const unsigned int *list_count;  // optional device-side length of node_list
+    int list_n;
     int sa_cap;      // floats of shared memory available for the search area
     float min_dn;    // smallest float >= 1e-10 (the reference compares against a double literal)
 };
@@ -215,8 +218,12 @@ __global__ void __launch_bounds__(kThreads) match_kernel(const MatchArgs a) {
             sh.cnt_ref = 0; sh.cnt_sa = 0; sh.list_len = 0; sh.m = 0;
         }
         __syncthreads();
-        const unsigned int g = sh.node;
-        if (g >= (unsigned int)a.n) break;
+        unsigned int g = sh.node;
+        if (a.node_list) {
+            const unsigned int lim = a.list_count ? *a.list_count : (unsigned int)a.list_n;
+            if (g >= lim) break;
+            g = (unsigned int)a.node_list[g];
+        } else if (g >= (unsigned int)a.n) break;
 
         // ---- node geometry ---------------------------------------------------------
         Node nd;
@@ -419,6 +426,7 @@ int launch_match(mimc3cu_ctx *ctx, const MatchLaunch &L) {
     a.off_u = L.off_u; a.off_v = L.off_v; a.csr_off = L.csr_off; a.piv = (const int2 *)L.piv; a.sign = L.sign;
     a.chips = L.chips; a.sareas = L.sareas; a.D = L.D; a.P = L.P;
     a.n = L.n; a.ocw = L.ocw; a.negate = L.negate; a.dp = L.dp; a.peak = (int2 *)L.peak; a.ncell = L.ncell;
+    a.node_list = L.node_list; a.list_count = L.list_count; a.list_n = L.list_n;
     a.sa_cap = (int)((smem - chip_bytes) / sizeof(float));
     a.min_dn = min_dn_float();
 
@@ -427,7 +435,9 @@ int launch_match(mimc3cu_ctx *ctx, const MatchLaunch &L) {
     CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, match_kernel, kThreads, smem));
     if (per_sm < 1) return mimc3cu_fail(ctx, "match: kernel does not fit on an SM (smem %zu)", smem);
     long long grid = (long long)per_sm * ctx->num_sms;
-    if (grid > L.n) grid = L.n;
+    const long long work = L.node_list ? (L.list_count ? (long long)L.n : (long long)L.list_n) : (long long)L.n;
+    if (grid > work) grid = work;
+    if (grid < 1) return 0;
 
     // per-CTA scratch: cmap values, flags, cell list
     long long stride = (L.max_cells + 15) & ~15LL;
@@ -438,7 +448,7 @@ int launch_match(mimc3cu_ctx *ctx, const MatchLaunch &L) {
     a.scr_list = (int *)(a.scr_val + (size_t)grid * stride);
     a.scr_flag = (unsigned char *)(a.scr_list + (size_t)grid * stride);
     a.scr_stride = stride;
-    a.counter = ctx->counter;
+    a.counter = ctx->counter;   // slot 0: the general kernel's node counter
     CU_CHECK(ctx, cudaMemsetAsync(ctx->counter, 0, sizeof(unsigned int), ctx->stream));
     match_kernel<<<(unsigned)grid, kThreads, smem, ctx->stream>>>(a);
     ctx->launches++;

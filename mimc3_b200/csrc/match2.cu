@@ -1,0 +1,652 @@
+// DLC-constrained, null-excluding NCC matcher, v2: exact FP32 arithmetic for sm_100a.
+//
+// Same contract as match.cu (matching_ncc_dlc_2 + extract_refchip + extract_sarea +
+// investigate_valid_grid + find_ncc_peak, MIMC_module.c:605-890) and the same bit-exact
+// results, for "exact-class" image pairs (sat.cu: non-negative multiples of 2^-3, which is
+// everything GMA_float_load_tiff / GMA_float_conv2 produce from integer DN).  What changed is
+// where the arithmetic runs:
+//
+//  * v1 accumulates five sums per pixel in FP64 and is bound by the F2F.F64.F32 conversion
+//    (16 lanes/clk/SM on B200, profiles/r01_ubench_sm100a.txt).
+//  * v2 observes that for a cell whose window and chip contain no null pixel the joint mask of
+//    MIMC_module.c:723 is all-ones, so n = S^2, sum(r), sum(r*r) are per-node constants and
+//    sum(s), sum(s*s) are window sums: all five come from the per-image summed-area tables
+//    (4 x 16-byte loads).  Only sum(fl(r*s)) needs the S^2 loop, and it is accumulated EXACTLY in
+//    FP32 with an error-free transformation (Fast2Sum against a running accumulator biased by a
+//    power of two A0 >= 16 * max product):
+//        p = r*s;  t = acc + p;  z = t - acc;  e = p - z;  acc = t;  lo += e
+//    i.e. 1 FMUL + 4 FADD per pixel on the FP32 pipes, no conversion.  acc stays in one binade
+//    [A0, 2*A0], so float_as_uint(acc) - float_as_uint(A0) is the partial sum in units of
+//    ulp(A0); lo is biased by 1.5*2^23 units the same way.  Both are then reduced as integers
+//    (REDUX.SUM), and the cell is normalised in FP64 with the reference's expression (:734).
+//  * Cells that touch a null pixel, the zero-filled border or the never-written last row/column
+//    of the search area are re-evaluated with the masked 5-sum FP64 loop.
+//
+// Work decomposition: a "group" of G threads owns one node at a time (G = 256, one CTA, for chip
+// half-widths 30/40; G = 32, one warp, for 7/15).  Thread (k, r) keeps the L pixels of chip row r,
+// segment k in REGISTERS; the search area is staged in shared memory with an odd pitch so that
+// the row-per-lane access pattern is bank-conflict free.  The reference's hill-climbing state
+// machine (pivot order, first-wins ties, "newly evaluated" stop rule, -2.0 placeholders) runs
+// verbatim in warp 0 of the group; the first 3x3 probe of every pivot is unconditional and is
+// evaluated up-front in batches of <= 32 cells.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr unsigned char kComputed = 1, kVisible = 2, kListed = 4;
+constexpr int kMaxJobs = 32;
+
+struct Match2Args {
+    const float *ref, *srch;
+    int H, W;
+    const ulonglong2 *sat_ref, *sat_srch;
+    double inv_ref, inv_ref2, inv_srch, inv_srch2;   // 2^-f, 4^-f of the two images
+    const int2 *node_uv;
+    int off_u, off_v;
+    const int *csr_off;
+    const int2 *piv;
+    int sign;
+    const int *node_list;
+    int n_list;
+    float negate;
+    float *dp;
+    int2 *peak;
+    int *ncell;
+    unsigned int *counter;          // dynamic node fetch for this launch
+    int *overflow_list;             // nodes that do not fit this launch's shared memory
+    unsigned int *overflow_count;
+    int sa_cap, cell_cap;           // per group: floats for the search area, cells of the cmap
+    float A0, Mlo;                  // accumulator biases
+    unsigned int A0_bits, Mlo_bits;
+    double hi_unit, lo_unit;
+    float min_dn;
+};
+
+struct Sums {
+    double sx, sy, sxx, syy, sxy;
+    int n;
+};
+
+template <int OCW, int G>
+struct Cfg {
+    static constexpr int S = 2 * OCW + 1;
+    static constexpr int NSEG = G / S;
+    static constexpr int L = (S + NSEG - 1) / NSEG;
+    static constexpr int NGROUPS = kThreads / G;
+    static constexpr int NWARPS = G / 32;
+    static_assert(NSEG >= 1, "group too small for this chip");
+    static_assert((L + 1) / 2 <= 16, "at most 16 pixels per FP32 accumulator");
+};
+
+template <int G>
+__device__ __forceinline__ void gsync() {
+    if (G == 32) __syncwarp();
+    else __syncthreads();
+}
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// (float)((n*sxy - sx*sy) / sqrt((n*sxx - sx*sx) * (n*syy - sy*sy)))   MIMC_module.c:734
+__device__ __forceinline__ float ncc_from_sums(const Sums &s) {
+    double n = (double)s.n;
+    double num = __dsub_rn(__dmul_rn(n, s.sxy), __dmul_rn(s.sx, s.sy));
+    double a = __dsub_rn(__dmul_rn(n, s.sxx), __dmul_rn(s.sx, s.sx));
+    double b = __dsub_rn(__dmul_rn(n, s.syy), __dmul_rn(s.sy, s.sy));
+    double den = __dsqrt_rn(__dmul_rn(a, b));
+    return __double2float_rn(__ddiv_rn(num, den));
+}
+
+// Window sums over image rows [y0,y1) x columns [x0,x1) (already clipped, possibly empty).
+__device__ __forceinline__ void rect_query(const ulonglong2 *sat, int W1, int x0, int y0, int x1, int y1,
+                                           unsigned long long &ss, unsigned long long &s, unsigned int &nul) {
+    if (x1 <= x0 || y1 <= y0) { ss = 0; s = 0; nul = 0; return; }
+    const ulonglong2 a = __ldg(&sat[(size_t)y1 * W1 + x1]), b = __ldg(&sat[(size_t)y0 * W1 + x1]);
+    const ulonglong2 c = __ldg(&sat[(size_t)y1 * W1 + x0]), d = __ldg(&sat[(size_t)y0 * W1 + x0]);
+    ss = a.x - b.x - c.x + d.x;
+    const unsigned long long pk = a.y - b.y - c.y + d.y;
+    s = pk >> 24;
+    nul = (unsigned int)(pk & 0xffffffull);
+}
+
+// 3x3 quadratic fit, MIMC_module.c:757-788, with the reference's float/double mix (H7).
+__device__ void subpixel_fit(const float n9[9], int peak_du, int peak_dv, float &du, float &dv) {
+#define FM(k, x) __fmul_rn((float)(k), (x))
+#define FA(x, y) __fadd_rn((x), (y))
+    float c0f = FA(FA(FA(FA(FA(FA(FA(FA(FM(6, n9[0]), -FM(12, n9[1])), FM(6, n9[2])), FM(6, n9[3])), -FM(12, n9[4])), FM(6, n9[5])), FM(6, n9[6])), -FM(12, n9[7])), FM(6, n9[8]));
+    float c1f = FA(FA(FA(FM(9, n9[0]), -FM(9, n9[2])), -FM(9, n9[6])), FM(9, n9[8]));
+    float c2f = FA(FA(FA(FA(FA(FA(FA(FA(FM(6, n9[0]), FM(6, n9[1])), FM(6, n9[2])), -FM(12, n9[3])), -FM(12, n9[4])), -FM(12, n9[5])), FM(6, n9[6])), FM(6, n9[7])), FM(6, n9[8]));
+    float c3f = FA(FA(FA(FA(FA(FM(-6, n9[0]), FM(6, n9[2])), -FM(6, n9[3])), FM(6, n9[5])), -FM(6, n9[6])), FM(6, n9[8]));
+    float c4f = FA(FA(FA(FA(FA(FM(-6, n9[0]), -FM(6, n9[1])), -FM(6, n9[2])), FM(6, n9[6])), FM(6, n9[7])), FM(6, n9[8]));
+#undef FM
+#undef FA
+    double c0 = __ddiv_rn((double)c0f, 36.0), c1 = __ddiv_rn((double)c1f, 36.0), c2 = __ddiv_rn((double)c2f, 36.0);
+    double c3 = __ddiv_rn((double)c3f, 36.0), c4 = __ddiv_rn((double)c4f, 36.0);
+    float fu = __double2float_rn(__dadd_rn(__dmul_rn(__dmul_rn(-2.0, c2), c3), __dmul_rn(c1, c4)));
+    float fv = __double2float_rn(__dadd_rn(__dmul_rn(__dmul_rn(-2.0, c0), c4), __dmul_rn(c1, c3)));
+    double det = __dsub_rn(__dmul_rn(__dmul_rn(4.0, c0), c2), __dmul_rn(c1, c1));
+    fu = __double2float_rn(__ddiv_rn((double)fu, det));
+    fv = __double2float_rn(__ddiv_rn((double)fv, det));
+    du = __fadd_rn(fu, (float)peak_du);
+    dv = __fadd_rn(fv, (float)peak_dv);
+}
+
+// Per-group control block in shared memory.
+template <int NWARPS>
+struct Ctl {
+    int job[kMaxJobs];               // cells of the current round
+    int2 part[NWARPS][kMaxJobs];     // per-warp integer partial sums (hi units, lo units)
+    Sums partd[NWARPS];              // masked-path partials
+    int m;                      // >0 fast round, <0 done, 0 unused
+    int mode;                   // 0 fast round, 1 masked round
+    unsigned int node;
+    int valid;
+    // chip constants from the reference SAT
+    unsigned long long chip_ss, chip_s;
+    int chip_fast;
+};
+
+template <int OCW, int G>
+__global__ void __launch_bounds__(kThreads, (G == 256 ? 3 : 2)) match2_kernel(const Match2Args a) {
+    using C = Cfg<OCW, G>;
+    constexpr int S = C::S, L = C::L;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ Ctl<C::NWARPS> ctl_all[C::NGROUPS];
+
+    const int tid = threadIdx.x;
+    const int grp = tid / G, t = tid - grp * G;
+    const int lane = tid & 31, gwarp = t >> 5;
+    Ctl<C::NWARPS> &ctl = ctl_all[grp];
+
+    // dynamic shared memory, per group: sa[sa_cap] floats | cval[cell_cap] floats | cflag[cell_cap] bytes
+    const size_t grp_bytes = (size_t)a.sa_cap * 4 + (size_t)a.cell_cap * 5;
+    float *sa = (float *)(smem_raw + grp * ((grp_bytes + 15) & ~(size_t)15));
+    float *cval = sa + a.sa_cap;
+    unsigned char *cflag = (unsigned char *)(cval + a.cell_cap);
+
+    // this thread's chip slice: row r, columns [col0, col0+len)
+    const int seg = t / S, r = t - seg * S;
+    const bool active = seg < C::NSEG;
+    const int col0 = seg * L;
+    const int len = active ? min(L, S - col0) : 0;
+    const int W1 = a.W + 1;
+
+    for (;;) {
+        gsync<G>();
+        if (t == 0) ctl.node = atomicAdd(a.counter, 1u);
+        gsync<G>();
+        const unsigned int idx = ctl.node;
+        if (idx >= (unsigned int)a.n_list) break;
+        const int g = a.node_list ? a.node_list[idx] : (int)idx;
+
+        // ---- node geometry (uniform over the group) -----------------------------------------
+        const int pb = a.csr_off[g], P = a.csr_off[g + 1] - pb;
+        const int2 *piv = a.piv + pb;
+        const int2 uv = a.node_uv[g];
+        const int u0 = uv.x, v0 = uv.y, su0 = uv.x + a.off_u, sv0 = uv.y + a.off_v;
+        if (P <= 0) {   // undefined behaviour in the reference (MIMC_module.c:589-591)
+            if (t == 0) {
+                a.dp[3 * (size_t)g] = CUDART_NAN_F; a.dp[3 * (size_t)g + 1] = CUDART_NAN_F; a.dp[3 * (size_t)g + 2] = -2.0f;
+                if (a.peak) a.peak[g] = make_int2(0, 0);
+                if (a.ncell) a.ncell[g] = 0;
+            }
+            continue;
+        }
+        const int2 last = piv[P - 1];
+        const int dx2 = abs(last.x) + OCW + 2, dy2 = abs(last.y) + OCW + 2;   // :863-866
+        const int Dx2 = 2 * dx2 + 1, Dy2 = 2 * dy2 + 1;
+        const int cw = Dx2 - 2 * OCW - 1, ch = Dy2 - 2 * OCW - 1;   // cells whose 3x3 probe can be requested
+        const int pitch = (Dx2 + 3) | 1;
+        if (Dy2 * pitch > a.sa_cap || cw * ch > a.cell_cap) {
+            if (t == 0) a.overflow_list[atomicAdd(a.overflow_count, 1u)] = g;
+            continue;
+        }
+
+        // ---- stage the chip through shared memory into registers (extract_refchip :845-855) ----
+        for (int i = t; i < S * S; i += G) {
+            const int rr = i / S, cc = i - rr * S;
+            const int iv = v0 + rr - OCW, iu = u0 + cc - OCW;
+            sa[i] = (iu >= 0 && iu < a.W && iv >= 0 && iv < a.H) ? __ldg(&a.ref[(size_t)iv * a.W + iu]) : 0.0f;
+        }
+        if (t < 32) {   // chip and search-area statistics from the SATs (investigate_valid_grid :605-644)
+            unsigned long long ss = 0, s = 0;
+            unsigned int nul = 0;
+            int area = 0, full = 0;
+            if (lane == 0) {
+                const int x0 = max(u0 - OCW, 0), y0 = max(v0 - OCW, 0), x1 = min(u0 + OCW + 1, a.W), y1 = min(v0 + OCW + 1, a.H);
+                rect_query(a.sat_ref, W1, x0, y0, x1, y1, ss, s, nul);
+                area = max(x1 - x0, 0) * max(y1 - y0, 0); full = S * S;
+            } else if (lane == 1) {   // written part of the search area: rows [0,Dy2-1) x columns [0,Dx2-1)
+                const int ax = su0 - dx2, ay = sv0 - dy2;
+                const int x0 = max(ax, 0), y0 = max(ay, 0), x1 = min(ax + Dx2 - 1, a.W), y1 = min(ay + Dy2 - 1, a.H);
+                rect_query(a.sat_srch, W1, x0, y0, x1, y1, ss, s, nul);
+                area = max(x1 - x0, 0) * max(y1 - y0, 0); full = Dx2 * Dy2;
+            }
+            const int cnt = (int)nul + (full - area);   // pixels < 1e-10, zero fill included
+            const int cnt_ref = __shfl_sync(0xffffffffu, cnt, 0), cnt_sa = __shfl_sync(0xffffffffu, cnt, 1);
+            if (lane == 0) {
+                ctl.valid = !(((float)cnt_ref / (float)(S * S) > 0.8f) || ((float)cnt_sa / (float)(Dx2 * Dy2) > 0.8f));
+                ctl.chip_ss = ss; ctl.chip_s = s;
+                ctl.chip_fast = (cnt == 0);
+            }
+        }
+        gsync<G>();
+        if (!ctl.valid) {
+            if (t == 0) {
+                a.dp[3 * (size_t)g] = CUDART_NAN_F; a.dp[3 * (size_t)g + 1] = CUDART_NAN_F; a.dp[3 * (size_t)g + 2] = -3.0f;
+                if (a.peak) a.peak[g] = make_int2(0, 0);
+                if (a.ncell) a.ncell[g] = 0;
+            }
+            continue;
+        }
+        float chip[L];
+#pragma unroll
+        for (int c = 0; c < L; c++) chip[c] = (c < len) ? sa[r * S + col0 + c] : 0.0f;
+        gsync<G>();
+
+        // ---- stage the search area (extract_sarea :857-890): zero outside the image, zero in the
+        //      never-written last row / column, zero in the pad columns [Dx2, pitch) ----------------
+        for (int y = gwarp; y < Dy2; y += C::NWARPS) {
+            const int iv = sv0 - dy2 + y;
+            const bool rowok = (y < Dy2 - 1) && iv >= 0 && iv < a.H;
+            const float *src = a.srch + (size_t)(rowok ? iv : 0) * a.W;
+            for (int x = lane; x < pitch; x += 32) {
+                const int iu = su0 - dx2 + x;
+                sa[y * pitch + x] = (rowok && x < Dx2 - 1 && iu >= 0 && iu < a.W) ? __ldg(&src[iu]) : 0.0f;
+            }
+        }
+        for (int i = t; i < cw * ch; i += G) cflag[i] = 0;
+        gsync<G>();
+
+        // ---- evaluation rounds driven by warp 0 of the group ---------------------------------------
+        // state of the reference's hill climb (registers, uniform over warp 0)
+        int ip_batch = 0, phase = 0;              // phase 0: up-front first probes, 1: climb
+        int ip = 0, px = 0, py = 0, duv0 = -1, duv1 = -1, flag_new = 1;
+        int peak_x = dx2, peak_y = dy2, ncells = 0;
+        float nccmax = -2.0f, best = -2.0f;
+        bool in_pivot = false;
+        int nslow = 0;                            // masked-path cells pending in ctl.job[0..nslow)
+
+        for (;;) {
+            if (gwarp == 0) {
+                int m = 0, mode = 0;
+                if (nslow > 0) {
+                    // masked re-evaluation of the cells the fast path could not take
+                    mode = 1; m = nslow;   // ctl.job[0..nslow) was filled by the finalize step below
+                    nslow = 0;
+                } else {
+                    if (phase == 0) {
+                        while (ip_batch < P && m <= kMaxJobs - 9) {
+                            const int2 pv = piv[ip_batch];
+                            const int bx = a.sign * pv.x + dx2, by = a.sign * pv.y + dy2;
+                            ip_batch++;
+                            if (bx - OCW <= 1 || bx + OCW >= Dx2 - 1 || by - OCW <= 1 || by + OCW >= Dy2 - 1) continue;
+                            bool want = false;
+                            int cell = 0;
+                            if (lane < 9) {
+                                cell = (by + (lane % 3 - 1) - OCW - 1) * cw + (bx + (lane / 3 - 1) - OCW - 1);
+                                want = !(cflag[cell] & (kComputed | kListed));
+                            }
+                            const unsigned int wm = __ballot_sync(0xffffffffu, want);
+                            if (want) {
+                                ctl.job[m + __popc(wm & ((1u << lane) - 1u))] = cell;
+                                cflag[cell] |= kListed;
+                            }
+                            m += __popc(wm);
+                            __syncwarp();
+                        }
+                        if (m == 0 && ip_batch >= P) phase = 1;
+                    }
+                    if (phase == 1) {
+                        // the reference's state machine, MIMC_module.c:691-753
+                        for (;;) {
+                            if (!in_pivot) {
+                                if (ip >= P) { m = -1; break; }
+                                const int2 pv = piv[ip];
+                                px = a.sign * pv.x + dx2; py = a.sign * pv.y + dy2;   // :693-694
+                                nccmax = -2.0f; duv0 = -1; duv1 = -1; flag_new = 1;
+                                in_pivot = true;
+                            }
+                            bool stop = !((duv0 != 0 || duv1 != 0) && flag_new != 0);       // :699
+                            if (!stop && (px - OCW <= 1 || px + OCW >= Dx2 - 1 || py - OCW <= 1 || py + OCW >= Dy2 - 1)) {
+                                duv0 = 0; duv1 = 0; stop = true;                             // :701-707 (break)
+                            }
+                            if (stop) {
+                                if (nccmax > best) { peak_x = px; peak_y = py; best = nccmax; }   // :747-752
+                                in_pivot = false; ip++;
+                                continue;
+                            }
+                            // lane k < 9 looks at probe cell k = (c1+1)*3 + (c2+1)  (c1: u outer, c2: v inner)
+                            int cell = 0;
+                            unsigned char f = kComputed;
+                            float v = 0.0f;
+                            if (lane < 9) {
+                                cell = (py + (lane % 3 - 1) - OCW - 1) * cw + (px + (lane / 3 - 1) - OCW - 1);
+                                f = cflag[cell];
+                                v = cval[cell];
+                            }
+                            const bool need = !(f & (kVisible | kComputed));
+                            const unsigned int nm = __ballot_sync(0xffffffffu, need);
+                            if (nm) {
+                                if (need) ctl.job[__popc(nm & ((1u << lane) - 1u))] = cell;
+                                m = __popc(nm);
+                                break;
+                            }
+                            const bool isnew = lane < 9 && (!(f & kVisible) || v < -1.0f);   // `cmap < -1.0` => evaluated now, :713
+                            const unsigned int newm = __ballot_sync(0xffffffffu, isnew);
+                            if (isnew) cflag[cell] = f | kVisible;
+                            flag_new = __popc(newm); ncells += flag_new;
+                            duv0 = 0; duv1 = 0;
+#pragma unroll
+                            for (int k = 0; k < 9; k++) {
+                                const float vk = __shfl_sync(0xffffffffu, v, k);
+                                if (vk > nccmax) { nccmax = vk; duv0 = k / 3 - 1; duv1 = k % 3 - 1; }   // :736-741
+                            }
+                            px += duv0; py += duv1;                                            // :744-745
+                            __syncwarp();
+                        }
+                    }
+                }
+                if (lane == 0) { ctl.m = m; ctl.mode = mode; }
+            }
+            gsync<G>();
+            const int m = ctl.m, mode = ctl.mode;
+            if (m < 0) break;
+            if (m == 0) continue;   // batch produced nothing new; warp 0 switches to the climb
+
+            if (mode == 0) {
+                // ---- fast round: sum(fl(r*s)) for m cells, exact in FP32 ------------------------------
+                // SAT corner loads for cell `lane` are issued first so their latency hides behind the loop
+                unsigned long long w_ss = 0, w_s = 0;
+                unsigned int w_nul = 1;
+                bool w_inside = false;
+                if (gwarp == 0 && lane < m) {
+                    const int cell = ctl.job[lane];
+                    const int cy = cell / cw, cx = cell - cy * cw;
+                    const int x0 = cx + 1, y0 = cy + 1;                       // window origin in the search area
+                    const int ix0 = su0 - dx2 + x0, iy0 = sv0 - dy2 + y0;     // ... and in the image
+                    w_inside = (x0 + S - 1 <= Dx2 - 2) && (y0 + S - 1 <= Dy2 - 2) && ix0 >= 0 && iy0 >= 0 &&
+                               ix0 + S <= a.W && iy0 + S <= a.H;
+                    if (w_inside) rect_query(a.sat_srch, W1, ix0, iy0, ix0 + S, iy0 + S, w_ss, w_s, w_nul);
+                }
+                for (int c = 0; c < m; c++) {
+                    const int cell = ctl.job[c];
+                    const int cy = cell / cw, cx = cell - cy * cw;
+                    unsigned int hi = 0;
+                    int lo = 0;
+                    if (active) {
+                        const float *sp = sa + (cy + 1 + r) * pitch + (cx + 1 + col0);
+                        float acc0 = a.A0, acc1 = a.A0, lo0 = a.Mlo, lo1 = a.Mlo;
+#pragma unroll
+                        for (int k = 0; k < L; k++) {
+                            const float p = __fmul_rn(chip[k], sp[k]);
+                            if (k & 1) {
+                                const float s1 = __fadd_rn(acc1, p);
+                                const float z = __fsub_rn(s1, acc1);
+                                lo1 = __fadd_rn(lo1, __fsub_rn(p, z));
+                                acc1 = s1;
+                            } else {
+                                const float s1 = __fadd_rn(acc0, p);
+                                const float z = __fsub_rn(s1, acc0);
+                                lo0 = __fadd_rn(lo0, __fsub_rn(p, z));
+                                acc0 = s1;
+                            }
+                        }
+                        hi = (__float_as_uint(acc0) - a.A0_bits) + (__float_as_uint(acc1) - a.A0_bits);
+                        lo = (int)(__float_as_uint(lo0) - a.Mlo_bits) + (int)(__float_as_uint(lo1) - a.Mlo_bits);
+                    }
+                    hi = __reduce_add_sync(0xffffffffu, hi);
+                    lo = __reduce_add_sync(0xffffffffu, lo);
+                    if (lane == 0) ctl.part[gwarp][c] = make_int2((int)hi, lo);
+                }
+                gsync<G>();
+                // ---- finalize: lane c of warp 0 normalises cell c --------------------------------------
+                if (gwarp == 0) {
+                    bool slowc = false;
+                    int cell = 0;
+                    if (lane < m) {
+                        cell = ctl.job[lane];
+                        if (ctl.chip_fast && w_inside && w_nul == 0) {
+                            long long hs = 0, ls = 0;
+#pragma unroll
+                            for (int w = 0; w < C::NWARPS; w++) {
+                                const int2 q = ctl.part[w][lane];
+                                hs += (unsigned int)q.x; ls += q.y;
+                            }
+                            Sums s;
+                            s.n = S * S;
+                            s.sxy = (double)hs * a.hi_unit + (double)ls * a.lo_unit;
+                            s.sx = (double)ctl.chip_s * a.inv_ref; s.sxx = (double)ctl.chip_ss * a.inv_ref2;
+                            s.sy = (double)w_s * a.inv_srch; s.syy = (double)w_ss * a.inv_srch2;
+                            cval[cell] = ncc_from_sums(s);
+                            cflag[cell] |= kComputed;
+                        } else {
+                            slowc = true;
+                        }
+                    }
+                    const unsigned int sm = __ballot_sync(0xffffffffu, slowc);
+                    __syncwarp();
+                    if (slowc) ctl.job[__popc(sm & ((1u << lane) - 1u))] = cell;   // compacted in place (index <= lane)
+                    nslow = __popc(sm);
+                    __syncwarp();
+                }
+            } else {
+                // ---- masked round: the reference's 5-sum loop with null exclusion (:719-733), FP64 ------
+                for (int c = 0; c < m; c++) {
+                    const int cell = ctl.job[c];
+                    const int cy = cell / cw, cx = cell - cy * cw;
+                    Sums s = {0.0, 0.0, 0.0, 0.0, 0.0, 0};
+                    if (active) {
+                        const float *sp = sa + (cy + 1 + r) * pitch + (cx + 1 + col0);
+#pragma unroll
+                        for (int k = 0; k < L; k++) {
+                            const float rv = chip[k], sv = sp[k];
+                            if (rv >= a.min_dn && sv >= a.min_dn) {   // null exclusion, :723
+                                s.n++;
+                                s.sx += (double)rv; s.sy += (double)sv;
+                                s.sxx += (double)__fmul_rn(rv, rv);
+                                s.syy += (double)__fmul_rn(sv, sv);
+                                s.sxy += (double)__fmul_rn(rv, sv);
+                            }
+                        }
+                    }
+                    s.n = __reduce_add_sync(0xffffffffu, s.n);
+                    s.sx = warp_sum_d(s.sx); s.sy = warp_sum_d(s.sy);
+                    s.sxx = warp_sum_d(s.sxx); s.syy = warp_sum_d(s.syy); s.sxy = warp_sum_d(s.sxy);
+                    if (G == 32) {
+                        if (lane == 0) { cval[cell] = ncc_from_sums(s); cflag[cell] |= kComputed; }
+                    } else {
+                        if (lane == 0) ctl.partd[gwarp] = s;
+                        gsync<G>();
+                        if (t == 0) {
+                            Sums q = ctl.partd[0];
+                            for (int w = 1; w < C::NWARPS; w++) {
+                                const Sums &z = ctl.partd[w];
+                                q.n += z.n; q.sx += z.sx; q.sy += z.sy; q.sxx += z.sxx; q.syy += z.syy; q.sxy += z.sxy;
+                            }
+                            cval[cell] = ncc_from_sums(q);
+                            cflag[cell] |= kComputed;
+                        }
+                        gsync<G>();
+                    }
+                }
+                if (G == 32) __syncwarp();
+            }
+        }
+
+        // ---- sub-pixel fit and output (:757-788) ------------------------------------------------------
+        if (t == 0) {
+            float n9[9];
+            for (int rr = 0; rr < 3; rr++)
+                for (int cc = 0; cc < 3; cc++) {
+                    const int cx = peak_x - 1 + cc - (OCW + 1), cy = peak_y - 1 + rr - (OCW + 1);
+                    float v = -2.0f;   // never evaluated (or outside the evaluable region)
+                    if (cx >= 0 && cx < cw && cy >= 0 && cy < ch) {
+                        const int cell = cy * cw + cx;
+                        if (cflag[cell] & kVisible) v = cval[cell];
+                    }
+                    n9[rr * 3 + cc] = v;
+                }
+            float du, dv;
+            subpixel_fit(n9, peak_x - dx2, peak_y - dy2, du, dv);
+            a.dp[3 * (size_t)g] = a.negate * du;
+            a.dp[3 * (size_t)g + 1] = a.negate * dv;
+            a.dp[3 * (size_t)g + 2] = best;
+            if (a.peak) a.peak[g] = make_int2(peak_x - dx2, peak_y - dy2);
+            if (a.ncell) a.ncell[g] = ncells;
+        }
+    }
+}
+
+float min_dn_float() {
+    float f = (float)1e-10;
+    if ((double)f < 1e-10) f = nextafterf(f, 1.0f);
+    return f;
+}
+
+template <int OCW, int G>
+int launch_one(mimc3cu_ctx *ctx, Match2Args &a, int per_sm_target, size_t smem, int n_list) {
+    auto kern = match2_kernel<OCW, G>;
+    CU_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+    if (per_sm < 1) return mimc3cu_fail(ctx, "match2: kernel does not fit on an SM (smem %zu)", smem);
+    (void)per_sm_target;
+    long long grid = (long long)per_sm * ctx->num_sms;
+    const long long groups = ((long long)n_list + Cfg<OCW, G>::NGROUPS - 1) / Cfg<OCW, G>::NGROUPS;
+    if (grid > groups) grid = groups;
+    kern<<<(unsigned)grid, kThreads, smem, ctx->stream>>>(a);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
+
+inline int group_size(int ocw) { return ocw >= 30 ? 256 : 32; }
+// resident CTAs per SM that bin k is sized for
+inline int bin_ctas(int G, int k) { return G == 256 ? 3 - k : (k == 0 ? 4 : (k == 1 ? 2 : 1)); }
+
+}  // namespace
+
+bool match2_supported(const MatchLaunch &L, const Image *ref, const Image *srch) {
+    if (!L.csr_off || L.chips) return false;                       // explicit (CP) mode stays on the general kernel
+    if (!(L.ocw == 7 || L.ocw == 15 || L.ocw == 30 || L.ocw == 40)) return false;
+    if (!ref->exact_class || !srch->exact_class || !ref->sat_valid || !srch->sat_valid) return false;
+    // exactness budget of the FP32 accumulation (see the header): product bits + fraction bits <= 37
+    const double maxprod = (double)ref->max_value * (double)srch->max_value;
+    int b = 0;
+    while (ldexp(1.0, b) < maxprod) b++;
+    return b + ref->frac_bits + srch->frac_bits <= 37;
+}
+
+// Per-launch shared-memory classes: bin k holds the nodes that fit when bin_ctas(G, k) CTAs share an SM.
+static void build_bins(mimc3cu_ctx *ctx, PivotSet *ps, PivotSet::Bins &B, int ocw) {
+    const int G = group_size(ocw), ngroups = kThreads / G;
+    const size_t usable = ctx->smem_optin;
+    for (int k = 0; k < 3; k++) {
+        const int ctas = bin_ctas(G, k);
+        size_t per_cta = (228 * 1024 - ctas * 1024) / ctas;          // 1 KB reserved per resident CTA
+        per_cta = std::min(per_cta, usable) - 4608;                  // static control blocks
+        const size_t per_group = (per_cta / ngroups) & ~(size_t)15;
+        // split: cells get 1/8 of the bytes (5 B each), the search area the rest
+        B.cell_cap[k] = (int64_t)((per_group / 8) / 5) & ~15LL;
+        B.sa_cap[k] = (int64_t)((per_group - B.cell_cap[k] * 5) / 4) & ~3LL;
+    }
+    std::vector<int32_t> lists[4];
+    for (int32_t g = 0; g < ps->n; g++) {
+        const int64_t Dx2 = 2 * (ps->last_u[g] + ocw + 2) + 1, Dy2 = 2 * (ps->last_v[g] + ocw + 2) + 1;
+        const int64_t pitch = (Dx2 + 3) | 1, need_sa = Dy2 * pitch, need_cells = (Dx2 - 2 * ocw - 1) * (Dy2 - 2 * ocw - 1);
+        int k = 0;
+        while (k < 3 && (need_sa > B.sa_cap[k] || need_cells > B.cell_cap[k])) k++;
+        lists[k].push_back(g);
+    }
+    std::vector<int32_t> all;
+    for (int k = 0; k < 4; k++) {
+        B.start[k] = (int32_t)all.size();
+        B.count[k] = (int32_t)lists[k].size();
+        all.insert(all.end(), lists[k].begin(), lists[k].end());
+    }
+    if (B.lists) cudaFree(B.lists);
+    cudaMalloc(&B.lists, sizeof(int32_t) * std::max<size_t>(all.size(), 1));
+    cudaMemcpy(B.lists, all.data(), sizeof(int32_t) * all.size(), cudaMemcpyHostToDevice);
+    B.ocw = ocw;
+}
+
+int launch_match2(mimc3cu_ctx *ctx, const MatchLaunch &L, const Image *ref, const Image *srch, PivotSet *ps) {
+    if (L.n <= 0) return 0;
+    // bins cached per (pivot set, ocw); two cache entries cover main's usage (one ocw per slot)
+    PivotSet::Bins *B = nullptr;
+    for (auto &b : ps->bins) if (b.ocw == L.ocw) B = &b;
+    if (!B) {
+        B = ps->bins[0].ocw < 0 ? &ps->bins[0] : &ps->bins[1];
+        CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        build_bins(ctx, ps, *B, L.ocw);
+    }
+    if (ctx->overflow_cap < (size_t)L.n) {
+        CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->overflow_list) CU_CHECK(ctx, cudaFree(ctx->overflow_list));
+        CU_CHECK(ctx, cudaMalloc(&ctx->overflow_list, sizeof(int) * (size_t)L.n));
+        ctx->overflow_cap = (size_t)L.n;
+    }
+
+    Match2Args a;
+    a.ref = L.ref; a.srch = L.srch; a.H = L.H; a.W = L.W;
+    a.sat_ref = (const ulonglong2 *)ref->sat; a.sat_srch = (const ulonglong2 *)srch->sat;
+    a.inv_ref = ldexp(1.0, -ref->frac_bits); a.inv_ref2 = ldexp(1.0, -2 * ref->frac_bits);
+    a.inv_srch = ldexp(1.0, -srch->frac_bits); a.inv_srch2 = ldexp(1.0, -2 * srch->frac_bits);
+    a.node_uv = L.node_uv; a.off_u = L.off_u; a.off_v = L.off_v; a.csr_off = L.csr_off; a.piv = (const int2 *)L.piv;
+    a.sign = L.sign; a.negate = L.negate; a.dp = L.dp; a.peak = (int2 *)L.peak; a.ncell = L.ncell;
+    a.min_dn = min_dn_float();
+    // accumulator biases: A0 = 2^(b+4) with 2^b >= max product; lo unit = product granularity
+    const double maxprod = std::max(1.0, (double)ref->max_value * (double)srch->max_value);
+    int b = 0;
+    while (ldexp(1.0, b) < maxprod) b++;
+    a.A0 = (float)ldexp(1.0, b + 4);
+    a.lo_unit = ldexp(1.0, -(ref->frac_bits + srch->frac_bits));
+    a.Mlo = (float)(ldexp(1.5, 23) * a.lo_unit);
+    a.hi_unit = ldexp(1.0, b + 4 - 23);
+    memcpy(&a.A0_bits, &a.A0, 4); memcpy(&a.Mlo_bits, &a.Mlo, 4);
+
+    // counters: [0] general kernel, [1..3] the v2 bins, [8] overflow count (seeded with bin 3)
+    CU_CHECK(ctx, cudaMemsetAsync(ctx->counter, 0, 16 * sizeof(unsigned int), ctx->stream));
+    a.overflow_list = ctx->overflow_list; a.overflow_count = ctx->counter + 8;
+    if (B->count[3] > 0) {
+        CU_CHECK(ctx, cudaMemcpyAsync(ctx->overflow_list, B->lists + B->start[3], sizeof(int) * (size_t)B->count[3],
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+        unsigned int c3 = (unsigned int)B->count[3];
+        // small H2D from the stack is safe: the value is copied at enqueue time for pageable memory
+        CU_CHECK(ctx, cudaMemcpyAsync(ctx->counter + 8, &c3, sizeof(c3), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const int G = group_size(L.ocw), ngroups = kThreads / G;
+    for (int k = 0; k < 3; k++) {
+        if (B->count[k] == 0) continue;
+        a.node_list = B->lists + B->start[k]; a.n_list = B->count[k];
+        a.counter = ctx->counter + 1 + k;
+        a.sa_cap = (int)B->sa_cap[k]; a.cell_cap = (int)B->cell_cap[k];
+        const size_t grp_bytes = (((size_t)a.sa_cap * 4 + (size_t)a.cell_cap * 5) + 15) & ~(size_t)15;
+        const size_t smem = grp_bytes * ngroups;
+        int rc = 0;
+        switch (L.ocw) {
+            case 7: rc = launch_one<7, 32>(ctx, a, 3 - k, smem, a.n_list); break;
+            case 15: rc = launch_one<15, 32>(ctx, a, 3 - k, smem, a.n_list); break;
+            case 30: rc = launch_one<30, 256>(ctx, a, 3 - k, smem, a.n_list); break;
+            case 40: rc = launch_one<40, 256>(ctx, a, 3 - k, smem, a.n_list); break;
+            default: return mimc3cu_fail(ctx, "match2: unsupported ocw %d", L.ocw);
+        }
+        if (rc) return rc;
+    }
+    // whatever did not fit goes to the general kernel (device-side count)
+    MatchLaunch L1 = L;
+    L1.node_list = ctx->overflow_list; L1.list_count = ctx->counter + 8; L1.list_n = 0;
+    if (B->count[3] == 0) {
+        // nothing pre-seeded and the v2 kernels only overflow if host and device sizing disagree;
+        // still run a minimal grid so that such nodes are never dropped
+        L1.n = std::min<int32_t>(L.n, ctx->num_sms);
+    }
+    return launch_match(ctx, L1);
+}

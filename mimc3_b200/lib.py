@@ -77,6 +77,9 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "mimc3cu_free": (C.c_int, [vp, vp]),
         "mimc3cu_memcpy_d2h": (C.c_int, [vp, vp, vp, C.c_size_t]),
         "mimc3cu_memcpy_h2d": (C.c_int, [vp, vp, vp, C.c_size_t]),
+        "mimc3cu_set_matcher": (C.c_int, [vp, i32]),
+        "mimc3cu_last_matcher": (C.c_int, [vp]),
+        "mimc3cu_image_class": (C.c_int, [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(f32)]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)
@@ -96,7 +99,7 @@ EXPORTED_SYMBOLS = (
     "mimc3cu_find_ncc_peak_batch", "mimc3cu_multimatch_async", "mimc3cu_cluster_async", "mimc3cu_postprocess",
     "mimc3cu_postprocess_stage", "mimc3cu_finalize", "mimc3cu_fp32_peak", "mimc3cu_timing_enable",
     "mimc3cu_timing_read", "mimc3cu_malloc", "mimc3cu_free", "mimc3cu_memcpy_d2h",
-    "mimc3cu_memcpy_h2d",
+    "mimc3cu_memcpy_h2d", "mimc3cu_set_matcher", "mimc3cu_last_matcher", "mimc3cu_image_class",
 )
 
 
@@ -236,6 +239,20 @@ class Context:
         self._ck(self.L.mimc3cu_set_pivots(self.h, slot, _ptr(off), _ptr(piv), off.shape[0] - 1))
 
     # matcher -------------------------------------------------------------------------------------
+    def set_matcher(self, mode):
+        """0 auto, 1 general FP64 kernel, 2 require the exact-FP32 kernel (also 'auto'/'v1'/'v2')."""
+        mode = {"auto": 0, "v1": 1, "general": 1, "v2": 2}.get(mode, mode)
+        self._ck(self.L.mimc3cu_set_matcher(self.h, int(mode)))
+
+    def last_matcher(self) -> int:
+        return int(self.L.mimc3cu_last_matcher(self.h))
+
+    def image_class(self, handle):
+        """(exact_class, frac_bits, max_value) of an image as the matcher sees it."""
+        a = C.c_int32(); b = C.c_int32(); m = C.c_float()
+        self._ck(self.L.mimc3cu_image_class(self.h, handle, C.byref(a), C.byref(b), C.byref(m)))
+        return bool(a.value), b.value, m.value
+
     def match(self, ref_img, search_img, offset, slot, sign, ocw, negate=False):
         """Synchronous; returns host arrays dp (n,3), peak (n,2), ncell (n)."""
         n = self.n

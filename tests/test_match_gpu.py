@@ -14,7 +14,10 @@ from tests.util import VEC_OCW, mismatch_report, same_bits_nan_aware, small_scen
 pytestmark = pytest.mark.gpu
 
 
-def _run_both(gpu_ctx, orc, sc, a, b, offset, sign, ocw, slot=0):
+MATCHERS = ("v1", "v2")   # general FP64 kernel / exact-FP32 kernel with summed-area tables
+
+
+def _run_both(gpu_ctx, orc, sc, a, b, offset, sign, ocw, slot=0, matcher="v2"):
     H, W = a.shape
     p = lib.params_for(sc.xyuvav, sc.dimx, sc.dimy, sc.dt)
     off, piv = lib.get_uv_pivot(sc.xyuvav, sc.dt, p.mpp, ocw, H, W)
@@ -23,9 +26,12 @@ def _run_both(gpu_ctx, orc, sc, a, b, offset, sign, ocw, slot=0):
     gpu_ctx.set_nodes(sc.xyuvav)
     gpu_ctx.set_pivots(slot, off, piv)
     ia, ib = gpu_ctx.image_from(a), gpu_ctx.image_from(b)
+    gpu_ctx.set_matcher(matcher)
     try:
         dp, peak, ncell = gpu_ctx.match(ia, ib, offset, slot, sign, ocw)
+        assert gpu_ctx.last_matcher() == (2 if matcher == "v2" else 1)
     finally:
+        gpu_ctx.set_matcher("auto")
         gpu_ctx.image_destroy(ia); gpu_ctx.image_destroy(ib)
     dpo, peako, ncello = orc.match(a, b, sc.xyuvav, offset, off, piv, sign, ocw)
     return (dp, peak, ncell), (dpo, peako, ncello)
@@ -43,34 +49,38 @@ def _assert_parity(got, want, tag):
     assert same_bits_nan_aware(dp, dpo), tag + " not bit-identical: " + mismatch_report(dp, dpo)
 
 
+@pytest.mark.parametrize("matcher", MATCHERS)
 @pytest.mark.parametrize("ocw", VEC_OCW)
 @pytest.mark.parametrize("direction", ["fwd", "swapped"])
-def test_match_u8_with_null_wedge(gpu_ctx, orc, ocw, direction):
+def test_match_u8_with_null_wedge(gpu_ctx, orc, ocw, direction, matcher):
     sc = small_scene()
     i0, i1 = sc.i0.numpy(), sc.i1.numpy()
     offset = np.array(sc.offset, np.int32)
     if direction == "fwd":
-        got, want = _run_both(gpu_ctx, orc, sc, i0, i1, offset, +1, ocw)
+        got, want = _run_both(gpu_ctx, orc, sc, i0, i1, offset, +1, ocw, matcher=matcher)
     else:
-        got, want = _run_both(gpu_ctx, orc, sc, i1, i0, -offset, -1, ocw)
-    _assert_parity(got, want, f"u8 ocw={ocw} {direction}")
+        got, want = _run_both(gpu_ctx, orc, sc, i1, i0, -offset, -1, ocw, matcher=matcher)
+    _assert_parity(got, want, f"u8 ocw={ocw} {direction} {matcher}")
     assert (want[0][:, 2] == -3).sum() > 0 or ocw >= 30      # the wedge invalidates some small-chip nodes
 
 
-@pytest.mark.parametrize("ocw", (15, 40))
-def test_match_u16(gpu_ctx, orc, ocw):
+@pytest.mark.parametrize("matcher", MATCHERS)
+@pytest.mark.parametrize("ocw", (7, 15, 30, 40))
+def test_match_u16(gpu_ctx, orc, ocw, matcher):
     """uint16-range data: float products exceed 2^24 and are rounded like the reference's."""
     sc = small_scene(dtype="u16", seed=9, null_wedge=False)
     i0, i1 = sc.i0.numpy(), sc.i1.numpy()
     i0 = np.minimum(i0 * 3.9, 65535).round().astype(np.float32)    # reach DN > 60000
     i1 = np.minimum(i1 * 3.9, 65535).round().astype(np.float32)
     assert i0.max() > 60000
-    got, want = _run_both(gpu_ctx, orc, sc, i0, i1, np.array(sc.offset, np.int32), +1, ocw)
-    _assert_parity(got, want, f"u16 ocw={ocw}")
+    got, want = _run_both(gpu_ctx, orc, sc, i0, i1, np.array(sc.offset, np.int32), +1, ocw, matcher=matcher)
+    _assert_parity(got, want, f"u16 ocw={ocw} {matcher}")
 
 
+@pytest.mark.parametrize("matcher", MATCHERS)
+@pytest.mark.parametrize("ocw", (15, 40))
 @pytest.mark.parametrize("kid", (0, 1, 2))
-def test_match_on_filtered_images(gpu_ctx, orc, kid):
+def test_match_on_filtered_images(gpu_ctx, orc, kid, ocw, matcher):
     """conv2-filtered inputs (multiples of 1/8 for the Laplacian), CPU-filtered so that only
     the matcher is under test."""
     import oracle
@@ -78,27 +88,67 @@ def test_match_on_filtered_images(gpu_ctx, orc, kid):
     i0, i1 = sc.i0.numpy(), sc.i1.numpy()
     c0 = np.zeros_like(i0); c1 = np.zeros_like(i1)
     orc.conv2(i0, kid, c0); orc.conv2(i1, kid, c1)
-    got, want = _run_both(gpu_ctx, orc, sc, c0, c1, np.array(sc.offset, np.int32), +1, 15)
-    _assert_parity(got, want, f"filtered kernel {kid}")
+    got, want = _run_both(gpu_ctx, orc, sc, c0, c1, np.array(sc.offset, np.int32), +1, ocw, matcher=matcher)
+    _assert_parity(got, want, f"filtered kernel {kid} ocw={ocw} {matcher}")
 
 
-def test_match_fast_glacier_wide_windows(gpu_ctx, orc):
+@pytest.mark.parametrize("kid", (0, 2))
+def test_match_on_filtered_u16_images(gpu_ctx, orc, kid):
+    """14-bit DN filtered by d/dx and by the Laplacian (values up to 2^18 in units of 1/8):
+    still inside the exact-FP32 class (product bits + fraction bits <= 37)."""
+    sc = small_scene(dtype="u16", seed=23, null_wedge=True)
+    i0, i1 = sc.i0.numpy(), sc.i1.numpy()
+    c0 = np.zeros_like(i0); c1 = np.zeros_like(i1)
+    orc.conv2(i0, kid, c0); orc.conv2(i1, kid, c1)
+    for ocw in (15, 40):
+        got, want = _run_both(gpu_ctx, orc, sc, c0, c1, np.array(sc.offset, np.int32), +1, ocw, matcher="v2")
+        _assert_parity(got, want, f"filtered u16 kernel {kid} ocw={ocw}")
+
+
+def test_general_float_images_use_the_general_kernel(gpu_ctx, orc):
+    """Arbitrary float pixels are outside the exact class: auto mode must pick the FP64 kernel,
+    and requiring v2 must fail loudly rather than return inexact numbers."""
+    from mimc3_b200.lib import Mimc3CuError
+    sc = small_scene(seed=29, null_wedge=False)
+    i0 = (sc.i0.numpy() * np.float32(1.37)).astype(np.float32); i1 = (sc.i1.numpy() * np.float32(1.37)).astype(np.float32)
+    H, W = i0.shape
+    p = lib.params_for(sc.xyuvav, sc.dimx, sc.dimy, sc.dt)
+    off, piv = lib.get_uv_pivot(sc.xyuvav, sc.dt, p.mpp, 15, H, W)
+    gpu_ctx.set_nodes(sc.xyuvav); gpu_ctx.set_pivots(0, off, piv)
+    ia, ib = gpu_ctx.image_from(i0), gpu_ctx.image_from(i1)
+    try:
+        assert gpu_ctx.image_class(ia)[0] is False
+        gpu_ctx.match(ia, ib, np.zeros(2, np.int32), 0, +1, 15)
+        assert gpu_ctx.last_matcher() == 1
+        gpu_ctx.set_matcher("v2")
+        with pytest.raises(Mimc3CuError):
+            gpu_ctx.match(ia, ib, np.zeros(2, np.int32), 0, +1, 15)
+    finally:
+        gpu_ctx.set_matcher("auto")
+        gpu_ctx.image_destroy(ia); gpu_ctx.image_destroy(ib)
+
+
+@pytest.mark.parametrize("matcher", MATCHERS)
+def test_match_fast_glacier_wide_windows(gpu_ctx, orc, matcher):
     """Config-4-like: ~40 px a-priori displacement => ~80 pivots and search areas that do not
     fit the small-window fast sizes."""
     sc = small_scene(H=900, W=900, seed=33, peak_px=43.0, apriori_gain=0.9, spacing=41, null_wedge=False,
                      band_width_frac=0.2)
     i0, i1 = sc.i0.numpy(), sc.i1.numpy()
-    got, want = _run_both(gpu_ctx, orc, sc, i0, i1, np.array(sc.offset, np.int32), +1, 40)
-    assert want[2].max() > 200     # many evaluated cells
-    _assert_parity(got, want, "fast glacier ocw=40")
+    for ocw in (40, 15):
+        got, want = _run_both(gpu_ctx, orc, sc, i0, i1, np.array(sc.offset, np.int32), +1, ocw, matcher=matcher)
+        assert want[2].max() > 200     # many evaluated cells
+        _assert_parity(got, want, f"fast glacier ocw={ocw} {matcher}")
 
 
-def test_match_nodes_at_image_border(gpu_ctx, orc):
+@pytest.mark.parametrize("matcher", MATCHERS)
+def test_match_nodes_at_image_border(gpu_ctx, orc, matcher):
     """Search areas hanging over the image edge are zero-filled (extract_sarea boundary check)."""
     sc = small_scene(H=400, W=400, seed=41, null_wedge=False, margin=44, spacing=39, peak_px=9.0)
     i0, i1 = sc.i0.numpy(), sc.i1.numpy()
-    got, want = _run_both(gpu_ctx, orc, sc, i0, i1, np.array((7, -6), np.int32), +1, 40)
-    _assert_parity(got, want, "border nodes")
+    for ocw in (40, 7):
+        got, want = _run_both(gpu_ctx, orc, sc, i0, i1, np.array((7, -6), np.int32), +1, ocw, matcher=matcher)
+        _assert_parity(got, want, f"border nodes ocw={ocw} {matcher}")
 
 
 def test_find_ncc_peak_batch_cp_shape(gpu_ctx, orc):
