@@ -252,13 +252,25 @@ __global__ void __launch_bounds__(kThreads, (G == 256 ? 3 : 2)) match2_kernel(co
 
         // ---- stage the search area (extract_sarea :857-890): zero outside the image, zero in the
         //      never-written last row / column, zero in the pad columns [Dx2, pitch) ----------------
-        for (int y = gwarp; y < Dy2; y += C::NWARPS) {
-            const int iv = sv0 - dy2 + y;
-            const bool rowok = (y < Dy2 - 1) && iv >= 0 && iv < a.H;
-            const float *src = a.srch + (size_t)(rowok ? iv : 0) * a.W;
-            for (int x = lane; x < pitch; x += 32) {
-                const int iu = su0 - dx2 + x;
-                sa[y * pitch + x] = (rowok && x < Dx2 - 1 && iu >= 0 && iu < a.W) ? __ldg(&src[iu]) : 0.0f;
+        if (su0 - dx2 >= 0 && sv0 - dy2 >= 0 && su0 - dx2 + Dx2 - 1 <= a.W && sv0 - dy2 + Dy2 - 1 <= a.H) {
+            // written part entirely inside the image (the common case): no per-pixel bounds tests
+            const float *src0 = a.srch + (size_t)(sv0 - dy2) * a.W + (su0 - dx2);
+            for (int y = gwarp; y < Dy2 - 1; y += C::NWARPS) {
+                const float *src = src0 + (size_t)y * a.W;
+                float *dst = sa + y * pitch;
+                for (int x = lane; x < pitch; x += 32) dst[x] = (x < Dx2 - 1) ? __ldg(&src[x]) : 0.0f;
+            }
+            if (gwarp == (Dy2 - 1) % C::NWARPS)
+                for (int x = lane; x < pitch; x += 32) sa[(Dy2 - 1) * pitch + x] = 0.0f;
+        } else {
+            for (int y = gwarp; y < Dy2; y += C::NWARPS) {
+                const int iv = sv0 - dy2 + y;
+                const bool rowok = (y < Dy2 - 1) && iv >= 0 && iv < a.H;
+                const float *src = a.srch + (size_t)(rowok ? iv : 0) * a.W;
+                for (int x = lane; x < pitch; x += 32) {
+                    const int iu = su0 - dx2 + x;
+                    sa[y * pitch + x] = (rowok && x < Dx2 - 1 && iu >= 0 && iu < a.W) ? __ldg(&src[iu]) : 0.0f;
+                }
             }
         }
         for (int i = t; i < cw * ch; i += G) cflag[i] = 0;
@@ -295,7 +307,7 @@ __global__ void __launch_bounds__(kThreads, (G == 256 ? 3 : 2)) match2_kernel(co
                             }
                             const unsigned int wm = __ballot_sync(0xffffffffu, want);
                             if (want) {
-                                ctl.job[m + __popc(wm & ((1u << lane) - 1u))] = cell;
+                                ctl.job[m + __popc(wm & ((1u << lane) - 1u))] = ((by + (lane % 3 - 1) - OCW - 1) << 16) | (bx + (lane / 3 - 1) - OCW - 1);
                                 cflag[cell] |= kListed;
                             }
                             m += __popc(wm);
@@ -334,7 +346,7 @@ __global__ void __launch_bounds__(kThreads, (G == 256 ? 3 : 2)) match2_kernel(co
                             const bool need = !(f & (kVisible | kComputed));
                             const unsigned int nm = __ballot_sync(0xffffffffu, need);
                             if (nm) {
-                                if (need) ctl.job[__popc(nm & ((1u << lane) - 1u))] = cell;
+                                if (need) ctl.job[__popc(nm & ((1u << lane) - 1u))] = ((py + (lane % 3 - 1) - OCW - 1) << 16) | (px + (lane / 3 - 1) - OCW - 1);
                                 m = __popc(nm);
                                 break;
                             }
@@ -367,8 +379,8 @@ __global__ void __launch_bounds__(kThreads, (G == 256 ? 3 : 2)) match2_kernel(co
                 unsigned int w_nul = 1;
                 bool w_inside = false;
                 if (gwarp == 0 && lane < m) {
-                    const int cell = ctl.job[lane];
-                    const int cy = cell / cw, cx = cell - cy * cw;
+                    const int job = ctl.job[lane];
+                    const int cy = job >> 16, cx = job & 0xffff;
                     const int x0 = cx + 1, y0 = cy + 1;                       // window origin in the search area
                     const int ix0 = su0 - dx2 + x0, iy0 = sv0 - dy2 + y0;     // ... and in the image
                     w_inside = (x0 + S - 1 <= Dx2 - 2) && (y0 + S - 1 <= Dy2 - 2) && ix0 >= 0 && iy0 >= 0 &&
@@ -376,8 +388,8 @@ __global__ void __launch_bounds__(kThreads, (G == 256 ? 3 : 2)) match2_kernel(co
                     if (w_inside) rect_query(a.sat_srch, W1, ix0, iy0, ix0 + S, iy0 + S, w_ss, w_s, w_nul);
                 }
                 for (int c = 0; c < m; c++) {
-                    const int cell = ctl.job[c];
-                    const int cy = cell / cw, cx = cell - cy * cw;
+                    const int job = ctl.job[c];
+                    const int cy = job >> 16, cx = job & 0xffff;
                     unsigned int hi = 0;
                     int lo = 0;
                     if (active) {
@@ -409,9 +421,10 @@ __global__ void __launch_bounds__(kThreads, (G == 256 ? 3 : 2)) match2_kernel(co
                 // ---- finalize: lane c of warp 0 normalises cell c --------------------------------------
                 if (gwarp == 0) {
                     bool slowc = false;
-                    int cell = 0;
+                    int job = 0;
                     if (lane < m) {
-                        cell = ctl.job[lane];
+                        job = ctl.job[lane];
+                        const int cell = (job >> 16) * cw + (job & 0xffff);
                         if (ctl.chip_fast && w_inside && w_nul == 0) {
                             long long hs = 0, ls = 0;
 #pragma unroll
@@ -432,15 +445,16 @@ __global__ void __launch_bounds__(kThreads, (G == 256 ? 3 : 2)) match2_kernel(co
                     }
                     const unsigned int sm = __ballot_sync(0xffffffffu, slowc);
                     __syncwarp();
-                    if (slowc) ctl.job[__popc(sm & ((1u << lane) - 1u))] = cell;   // compacted in place (index <= lane)
+                    if (slowc) ctl.job[__popc(sm & ((1u << lane) - 1u))] = job;   // compacted in place (index <= lane)
                     nslow = __popc(sm);
                     __syncwarp();
                 }
             } else {
                 // ---- masked round: the reference's 5-sum loop with null exclusion (:719-733), FP64 ------
                 for (int c = 0; c < m; c++) {
-                    const int cell = ctl.job[c];
-                    const int cy = cell / cw, cx = cell - cy * cw;
+                    const int job = ctl.job[c];
+                    const int cy = job >> 16, cx = job & 0xffff;
+                    const int cell = cy * cw + cx;
                     Sums s = {0.0, 0.0, 0.0, 0.0, 0.0, 0};
                     if (active) {
                         const float *sp = sa + (cy + 1 + r) * pitch + (cx + 1 + col0);

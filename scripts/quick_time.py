@@ -4,6 +4,7 @@ sys.path.insert(0, '/root/repo')
 from mimc3_b200 import lib, synth
 wl = sys.argv[1] if len(sys.argv) > 1 else "c1"
 mode = sys.argv[2] if len(sys.argv) > 2 else "auto"
+ocws = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [7, 15, 30, 40]
 cfg = dict(c1=dict(H=2048, W=2048, dtype="u8", spacing=19), c2s=dict(H=4096, W=4096, dtype="u16", spacing=20))[wl]
 sc = synth.make_scene(seed=1, device="cuda", **cfg)
 ctx = lib.Context(0)
@@ -16,7 +17,7 @@ n = sc.n
 dp = torch.empty((n, 3), device="cuda"); nc = torch.empty(n, dtype=torch.int32, device="cuda")
 st = torch.cuda.ExternalStream(ctx.stream)
 tot = 0.0; flop = 0.0
-for slot, ocw in enumerate((7, 15, 30, 40)):
+for slot, ocw in enumerate(ocws):
     t = time.time(); off, piv = lib.get_uv_pivot(sc.xyuvav, sc.dt, p.mpp, ocw, H, W); tp = time.time() - t
     ctx.set_pivots(slot, off, piv)
     for rep in range(3):
