@@ -1,0 +1,82 @@
+"""CPU tests (no GPU) of the host side of the product: the C-ABI library loads and exports every
+symbol include/mimc3cu.h declares, its host-only entry points (pivot generation, defaults) agree
+with the oracle, and every compute entry point fails loudly without a CUDA device."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from mimc3_b200 import lib
+from tests.util import VEC_OCW, small_scene
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(mimc3cu_\w+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = lib.load_library()
+    syms = declared_symbols("mimc3cu.h")
+    assert len(syms) >= 35
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, missing
+    assert set(lib.EXPORTED_SYMBOLS) <= set(syms), sorted(set(lib.EXPORTED_SYMBOLS) - set(syms))
+    assert L.mimc3cu_version() == 100
+
+
+def test_default_params_are_the_reference_constants():
+    p = lib.default_params()
+    assert list(p.vec_ocw) == [7, 15, 30, 40]          # MIMC_main.c:134-137
+    assert p.AW_CRE == 10.0 and abs(p.AW_SF - 1.8) < 1e-6
+    assert p.radius_neighbor_dpf1 == 3.0 and p.radius_neighbor_ps == 5.0 and p.num_dp == 32
+
+
+@pytest.mark.parametrize("peak_px", (6.3, 43.0))
+def test_get_uv_pivot_host_matches_oracle(orc, peak_px):
+    """mimc3cu_get_uv_pivot is host code (like the reference's) and needs no GPU."""
+    sc = small_scene(H=900, W=700, seed=3, peak_px=peak_px, spacing=17, apriori_gain=0.9)
+    H, W = sc.shape
+    p = lib.params_for(sc.xyuvav, sc.dimx, sc.dimy, sc.dt)
+    for ocw in VEC_OCW:
+        off, piv = lib.get_uv_pivot(sc.xyuvav, sc.dt, p.mpp, ocw, H, W)
+        off_o, piv_o = orc.get_uv_pivot(sc.xyuvav, sc.dt, p.mpp, ocw, H, W)
+        assert np.array_equal(off, off_o) and np.array_equal(piv, piv_o)
+        assert (np.diff(off) >= 1).all()
+
+
+def test_get_uv_pivot_near_the_border_truncates(orc):
+    """The border test of MIMC_module.c:576-580 shortens pivot lines of nodes next to the edge."""
+    sc = small_scene(H=300, W=300, seed=4, peak_px=30.0, spacing=11, margin=44, apriori_gain=1.0)
+    H, W = sc.shape
+    p = lib.params_for(sc.xyuvav, sc.dimx, sc.dimy, sc.dt)
+    off, piv = lib.get_uv_pivot(sc.xyuvav, sc.dt, p.mpp, 40, H, W)
+    off_o, piv_o = orc.get_uv_pivot(sc.xyuvav, sc.dt, p.mpp, 40, H, W)
+    assert np.array_equal(off, off_o) and np.array_equal(piv, piv_o)
+    assert np.diff(off).min() < np.diff(off).max()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback_without_a_gpu():
+    L = lib.load_library()
+    assert L.mimc3cu_device_count() == 0
+    with pytest.raises(lib.Mimc3CuError) as e:
+        lib.Context(0)
+    assert "no CPU fallback" in str(e.value) or "no CUDA device" in str(e.value)
+
+
+def test_product_package_does_not_import_the_oracle():
+    """oracle/ is test infrastructure: nothing under mimc3_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "mimc3_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".c", ".h")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", txt, flags=re.M), os.path.join(dirpath, f)
+                assert "mimc3_oracle" not in txt, os.path.join(dirpath, f)
