@@ -50,6 +50,11 @@ typedef struct mimc3cu_params {
     float dt;                    /* days between the images                 :114 */
     int32_t dimx, dimy;          /* node grid                               :211-219 */
     int32_t num_dp;              /* attempts per node (32)                  :74 */
+    /* control-point stage, MIMC_main.c:165-168 */
+    int32_t num_cp_max;          /* 500 */
+    int32_t num_cp_min;          /* 50 */
+    float ratio_cp;              /* 0.03 */
+    float thres_spd_cp;          /* 10 m/yr */
 } mimc3cu_params;
 
 void mimc3cu_default_params(mimc3cu_params *p);
@@ -146,6 +151,19 @@ int mimc3cu_find_ncc_peak_batch(mimc3cu_ctx *ctx, const float *refchips, int32_t
  * ncell_dev (32, n) optional. i0c/i1c are scratch images for the filtered pair. */
 int mimc3cu_multimatch_async(mimc3cu_ctx *ctx, int32_t i0, int32_t i1, int32_t i0c, int32_t i1c,
                              const int32_t *offset, const mimc3cu_params *p, float *dp_dev, int32_t *ncell_dev);
+
+/* ---- control points --------------------------------------------------------------- */
+/* get_offset_image, MIMC_module.c:33-492: integer offset between the two images from slow
+ * ("control point") nodes.  xyuvav (n,6) on the host; kernels = the three filters of
+ * MIMC_main.c:175-196 (1x3, 3x1, 3x3, row-major); seed = what the reference passes to srand()
+ * (time(NULL), MIMC_module.c:516) -- the candidate permutation uses glibc rand() like the
+ * reference, so the same seed gives the same control points.
+ * Outputs: offset[2]; flag_cp[n] (caller-zeroed; set to 1 for nodes used as CPs); *result = 1
+ * (ok) or -1 (not enough control points: the reference's return value); num_cp_found optional.
+ * Returns 0 unless a CUDA error occurred. */
+int mimc3cu_get_offset_image(mimc3cu_ctx *ctx, int32_t i0, int32_t i1, const double *xyuvav, int32_t n,
+                             const mimc3cu_params *p, const float *k1x3, const float *k3x1, const float *k3x3,
+                             uint32_t seed, int32_t *offset, uint8_t *flag_cp, int32_t *result, int32_t *num_cp_found);
 
 /* ---- postprocess ---------------------------------------------------------------- */
 /* calc_mean_var_num_dp_cluster, MIMC_module.c:994-1194: dp_dev (num_dp, n, 3) ->

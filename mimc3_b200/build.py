@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmimc3cu.so")
-SOURCES = ["api.cu", "match.cu", "match2.cu", "sat.cu", "conv2.cu", "post.cu", "probe.cu"]
+SOURCES = ["api.cu", "match.cu", "match2.cu", "sat.cu", "cp.cu", "conv2.cu", "post.cu", "probe.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOST_CXX = "/usr/bin/g++"
 

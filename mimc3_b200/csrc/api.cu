@@ -118,6 +118,7 @@ void mimc3cu_default_params(mimc3cu_params *p) {
     p->radius_neighbor_ps = 5.0f;                                                      // :162
     p->dt = 16.0f;
     p->num_dp = 32;
+    p->num_cp_max = 500; p->num_cp_min = 50; p->ratio_cp = 0.03f; p->thres_spd_cp = 10.0f;            // :165-168
 }
 
 int mimc3cu_version(void) { return MIMC3CU_VERSION; }
@@ -498,6 +499,19 @@ int mimc3cu_multimatch_async(mimc3cu_ctx *ctx, int32_t i0, int32_t i1, int32_t i
         }
     }
     return 0;
+}
+
+/* ---- control points (cp.cu) ---------------------------------------------------------------- */
+int mimc3cu_get_offset_image(mimc3cu_ctx *ctx, int32_t i0, int32_t i1, const double *xyuvav, int32_t n, const mimc3cu_params *p,
+                             const float *k1x3, const float *k3x1, const float *k3x3, uint32_t seed, int32_t *offset,
+                             uint8_t *flag_cp, int32_t *result, int32_t *num_cp_found) {
+    Image *a = get_image(ctx, i0), *b = get_image(ctx, i1);
+    if (!a || !b) return mimc3cu_fail(ctx, "get_offset_image: bad image handle");
+    if (a->H != b->H || a->W != b->W) return mimc3cu_fail(ctx, "get_offset_image: the two images must have the same size");
+    if (!xyuvav || !p || !offset || !flag_cp || !result || n <= 0) return mimc3cu_fail(ctx, "get_offset_image: bad arguments");
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    return cp_get_offset_image(ctx, a, b, xyuvav, n, p, k1x3 ? k1x3 : kFilter[0], k3x1 ? k3x1 : kFilter[1], k3x3 ? k3x3 : kFilter[2],
+                               seed, offset, flag_cp, result, num_cp_found);
 }
 
 /* ---- postprocess (post.cu) ---------------------------------------------------------------- */

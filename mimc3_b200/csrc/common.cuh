@@ -117,6 +117,8 @@ struct MatchLaunch {
     // explicit mode (CP stage)
     const float *chips = nullptr, *sareas = nullptr;
     int32_t D = 0, P = 0;
+    int64_t chip_stride = 0;   // 0 => S*S (dense chips)
+    int32_t chip_pitch = 0;    // 0 => S
     // common
     int32_t n = 0, ocw = 0;
     float negate = 1.0f;
@@ -133,6 +135,11 @@ int launch_match(mimc3cu_ctx *ctx, const MatchLaunch &L);
 // match2.cu: exact-FP32 matcher for exact-class image pairs; falls back to launch_match per node
 int launch_match2(mimc3cu_ctx *ctx, const MatchLaunch &L, const Image *ref, const Image *srch, PivotSet *ps);
 bool match2_supported(const MatchLaunch &L, const Image *ref, const Image *srch);
+
+// cp.cu
+int cp_get_offset_image(mimc3cu_ctx *ctx, Image *i0, Image *i1, const double *xyuvav, int32_t n, const mimc3cu_params *p,
+                        const float *k1x3, const float *k3x1, const float *k3x3, uint32_t seed, int32_t *offset,
+                        uint8_t *flag_cp, int32_t *result, int32_t *num_cp_found);
 
 // sat.cu
 void image_invalidate(Image *im);

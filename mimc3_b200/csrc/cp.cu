@@ -1,0 +1,302 @@
+// Control-point (CP) stage: the integer image-to-image offset, get_offset_image
+// (MIMC_module.c:33-492) + GMA_double_randperm_row (:494-540).
+//
+// Flow of the reference, kept step for step (the candidate order, the glibc rand() permutation,
+// the float segment boundaries and the sequential float sums decide the result):
+//   candidates (a-priori speed < thres_spd_cp, <= 50 % null pixels in the 61x61 window of i0)
+//   -> random row permutation -> segments -> per segment, 4 image variants x chip half-widths
+//   {vec_ocw[1], vec_ocw[2]} x {forward, swapped} = 16 attempts with the shared (2*AW_CRE+1)^2
+//   rectangular pivot set on 85x85 tiles -> clusters -> clusters with support >= 0.6 are CPs.
+// On the GPU: the tiles of a segment are cut (and filtered) by one kernel launch per variant, the
+// 16 attempts run through the general matcher in its explicit-tile mode, clustering reuses the
+// postprocess kernel.  Only the candidate bookkeeping and the final sums stay on the host.
+//
+// Tile-local conv2 (:273-308): the reference filters an 87x87 window per node into ONE output
+// buffer reused for every node of the segment, so GMA_float_conv2's stale-border behaviour
+//  chains the nodes together: the right border column is shifted again at every
+// call and takes part in the next call's global minimum.  That recurrence is a scalar per
+// (image, variant) and is evaluated by cp_shift_scan_kernel in node order.
+#include <math_constants.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kT = 256;
+
+// number of pixels of the (2*ocw+1)^2 window of `img` around each node with value < 0.00001 (:100-103)
+__global__ void __launch_bounds__(kT) cp_nullcount_kernel(const float *__restrict__ img, int H, int W, const int2 *__restrict__ uv,
+                                                          int n, int ocw, int *__restrict__ count) {
+    const int g = blockIdx.x;
+    if (g >= n) return;
+    const int S = 2 * ocw + 1;
+    int c = 0;
+    for (int i = threadIdx.x; i < S * S; i += kT) {
+        const int r = i / S, q = i - r * S;
+        const int y = uv[g].y + r - ocw, x = uv[g].x + q - ocw;
+        if (x >= 0 && x < W && y >= 0 && y < H) c += ((double)__ldg(&img[(size_t)y * W + x]) < 0.00001) ? 1 : 0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&count[g], c);
+}
+
+__device__ __forceinline__ float px_or_zero(const float *img, int H, int W, int y, int x) {
+    return (x >= 0 && x < W && y >= 0 && y < H) ? __ldg(&img[(size_t)y * W + x]) : 0.0f;
+}
+// dn_in = (int32_t)(px + 0.5) ? px : NaN   (MIMC_module.c:2548)
+__device__ __forceinline__ float null_to_nan(float px) {
+    double t = (double)px + 0.5;
+    return (t > -1.0 && t < 1.0) ? CUDART_NAN_F : px;
+}
+
+// One CTA per (node, image): the T x T tile (T = 2*ocw_chip+1) of the raw image (variant < 0) or
+// of the tile-local filtered image before the shift; for filtered variants also the minimum over
+// the interior of the (T+2)^2 working window (the part GMA_float_conv2 writes).
+__global__ void __launch_bounds__(kT) cp_tiles_kernel(const float *__restrict__ i0, const float *__restrict__ i1, int H, int W,
+                                                      const int2 *__restrict__ uv, int nsub, int ocw_chip, int variant,
+                                                      const float *__restrict__ kern, int kh, int kw,
+                                                      float *__restrict__ tiles, float *__restrict__ mins) {
+    __shared__ float red[kT / 32];
+    const int g = blockIdx.x, im = blockIdx.y;
+    const float *img = im ? i1 : i0;
+    const int T = 2 * ocw_chip + 1, Tw = T + 2;
+    const int cu = uv[g].x, cv = uv[g].y;
+    float *tile = tiles + ((size_t)im * nsub + g) * T * T;
+    if (variant < 0) {
+        for (int i = threadIdx.x; i < T * T; i += kT) {
+            const int r = i / T, c = i - r * T;
+            tile[i] = px_or_zero(img, H, W, cv + r - ocw_chip, cu + c - ocw_chip);
+        }
+        return;
+    }
+    const int ocwx = kw / 2, ocwy = kh / 2;
+    float vmin = 1e+37f;
+    // working window coordinates (wr, wc) in [0, Tw); window pixel (wr, wc) = image (cv - ocw_chip - 1 + wr, ...)
+    for (int i = threadIdx.x; i < Tw * Tw; i += kT) {
+        const int wr = i / Tw, wc = i - wr * Tw;
+        if (wr < ocwy || wr >= Tw - ocwy || wc < ocwx || wc >= Tw - ocwx) continue;   // not written by the stencil loop
+        float sum = 0.0f;
+        for (int a = 0; a < kh; a++)
+            for (int b = 0; b < kw; b++) {
+                const float px = px_or_zero(img, H, W, cv - ocw_chip - 1 + wr + a - ocwy, cu - ocw_chip - 1 + wc + b - ocwx);
+                sum = __fadd_rn(sum, __fmul_rn(null_to_nan(px), kern[a * kw + b]));
+            }
+        vmin = fminf(vmin, sum);   // fminf drops NaN like the reference's `<` scan
+        if (wr >= 1 && wr <= T && wc >= 1 && wc <= T) tile[(wr - 1) * T + (wc - 1)] = sum;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = vmin;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kT / 32; w++) vmin = fminf(vmin, red[w]);
+        mins[(size_t)im * nsub + g] = vmin;
+    }
+}
+
+// The per-call global minimum of GMA_float_conv2 on the reused output buffer, in node order:
+// dn_min_k = min(interior_k, 0 [never-written cells], r_k [right border column, kernels with kw = 3]),
+// r_{k+1} = r_k - (dn_min_k - 1).  One thread per image.
+__global__ void cp_shift_scan_kernel(const float *__restrict__ mins, int nsub, int kw, float *__restrict__ shift) {
+    const int im = threadIdx.x;
+    if (im >= 2) return;
+    float r = 0.0f;
+    for (int k = 0; k < nsub; k++) {
+        float m = 1e+37f;
+        const float I = mins[(size_t)im * nsub + k];
+        if (I < m) m = I;
+        if (0.0f < m) m = 0.0f;
+        if (kw == 3 && r < m) m = r;
+        const float t = __fsub_rn(m, 1.0f);
+        shift[(size_t)im * nsub + k] = t;
+        if (kw == 3) r = __fsub_rn(r, t);
+    }
+}
+
+__global__ void __launch_bounds__(kT) cp_apply_shift_kernel(float *__restrict__ tiles, const float *__restrict__ shift, int nsub,
+                                                            int TT) {
+    const int g = blockIdx.x, im = blockIdx.y;
+    const float t = shift[(size_t)im * nsub + g];
+    float *tile = tiles + ((size_t)im * nsub + g) * TT;
+    for (int i = threadIdx.x; i < TT; i += kT) {
+        const float v = tile[i];
+        tile[i] = isnan(v) ? 0.0f : __fsub_rn(v, t);
+    }
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    template <typename T> T *as() { return (T *)p; }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+};
+
+}  // namespace
+
+int cp_get_offset_image(mimc3cu_ctx *ctx, Image *i0, Image *i1, const double *xyuvav, int32_t n, const mimc3cu_params *p,
+                        const float *k1x3, const float *k3x1, const float *k3x3, uint32_t seed, int32_t *offset,
+                        uint8_t *flag_cp, int32_t *result, int32_t *num_cp_found) {
+    const int H = i0->H, W = i0->W;
+    cudaStream_t st = ctx->stream;
+    *result = -1;
+    if (num_cp_found) *num_cp_found = 0;
+    const int ocw2 = p->vec_ocw[2];
+    const int ocw_chip = (int)((float)ocw2 + p->AW_CRE + 2.0f);   // :48 (int + float + int, truncated)
+    const int T = 2 * ocw_chip + 1;
+
+    // number of control points sought (:57-64)
+    int32_t num_cp;
+    if ((float)n * p->ratio_cp > (float)p->num_cp_max) num_cp = p->num_cp_max;
+    else num_cp = (int32_t)((float)n * p->ratio_cp);
+
+    // candidates: slow nodes (:71-83) ...
+    std::vector<int32_t> cand;
+    for (int32_t g = 0; g < n; g++) {
+        const float spd_sq = (float)(xyuvav[6 * (size_t)g + 4] * xyuvav[6 * (size_t)g + 4] + xyuvav[6 * (size_t)g + 5] * xyuvav[6 * (size_t)g + 5]);
+        if (spd_sq < p->thres_spd_cp * p->thres_spd_cp) cand.push_back(g);
+    }
+    // ... whose 61x61 window of i0 is at most half null (:86-121; the reference tests i0 twice)
+    if (!cand.empty()) {
+        std::vector<int2> uv(cand.size());
+        for (size_t k = 0; k < cand.size(); k++) {
+            uv[k].x = (int32_t)xyuvav[6 * (size_t)cand[k] + 2];
+            uv[k].y = (int32_t)xyuvav[6 * (size_t)cand[k] + 3];
+        }
+        DevBuf d_uv, d_cnt;
+        CU_CHECK(ctx, d_uv.alloc(sizeof(int2) * uv.size()));
+        CU_CHECK(ctx, d_cnt.alloc(sizeof(int) * uv.size()));
+        CU_CHECK(ctx, cudaMemcpyAsync(d_uv.p, uv.data(), sizeof(int2) * uv.size(), cudaMemcpyHostToDevice, st));
+        CU_CHECK(ctx, cudaMemsetAsync(d_cnt.p, 0, sizeof(int) * uv.size(), st));
+        cp_nullcount_kernel<<<(unsigned)uv.size(), kT, 0, st>>>(i0->d, H, W, d_uv.as<int2>(), (int)uv.size(), ocw2, d_cnt.as<int>());
+        ctx->launches++;
+        CU_CHECK(ctx, cudaGetLastError());
+        std::vector<int> cnt(uv.size());
+        CU_CHECK(ctx, cudaMemcpyAsync(cnt.data(), d_cnt.p, sizeof(int) * uv.size(), cudaMemcpyDeviceToHost, st));
+        CU_CHECK(ctx, cudaStreamSynchronize(st));
+        const int thres_numpx = (2 * ocw2 + 1) * (2 * ocw2 + 1) / 2;
+        std::vector<int32_t> keep;
+        for (size_t k = 0; k < cand.size(); k++)
+            if (!(cnt[k] > thres_numpx)) keep.push_back(cand[k]);
+        cand.swap(keep);
+    }
+    const int32_t num_cand = (int32_t)cand.size();
+    if (num_cand < p->num_cp_min) return 0;   // :130-135 (result stays -1)
+    if (num_cp > num_cand) num_cp = (int32_t)((float)num_cand * 0.75);   // :137-141 (float * double literal)
+    if (num_cp < 1) num_cp = 1;
+
+    // GMA_double_randperm_row (:494-540) on the candidate list, glibc srand/rand
+    {
+        std::vector<int32_t> tmp(cand), out(num_cand);
+        srand(seed);
+        for (int32_t lim = num_cand - 1; lim >= 0; lim--) {
+            const int32_t idx = lim != 0 ? (int32_t)(rand() % lim) : 0;
+            out[lim] = tmp[idx];
+            tmp[idx] = tmp[0];
+            tmp[0] = tmp[lim];
+        }
+        cand.swap(out);
+    }
+
+    // segments (:183-194)
+    const int32_t num_segment = (num_cand < p->num_cp_min) ? 1 : num_cand / num_cp;
+    std::vector<int32_t> seg(num_segment + 1);
+    seg[0] = 0;
+    for (int32_t c = 1; c <= num_segment; c++) seg[c] = (int32_t)((float)num_cand * ((float)c / (float)num_segment));
+
+    // shared rectangular pivot set (:165-176): u outer, v inner
+    const int R = (int)p->AW_CRE;
+    std::vector<int32_t> piv;
+    for (int a = -R; a <= R; a++)
+        for (int b = -R; b <= R; b++) { piv.push_back(a); piv.push_back(b); }
+    const int P = (int)piv.size() / 2;
+    DevBuf d_piv, d_kern;
+    CU_CHECK(ctx, d_piv.alloc(sizeof(int32_t) * piv.size()));
+    CU_CHECK(ctx, cudaMemcpyAsync(d_piv.p, piv.data(), sizeof(int32_t) * piv.size(), cudaMemcpyHostToDevice, st));
+    float kall[15];
+    memcpy(kall, k1x3, 3 * sizeof(float)); memcpy(kall + 3, k3x1, 3 * sizeof(float)); memcpy(kall + 6, k3x3, 9 * sizeof(float));
+    CU_CHECK(ctx, d_kern.alloc(sizeof(kall)));
+    CU_CHECK(ctx, cudaMemcpyAsync(d_kern.p, kall, sizeof(kall), cudaMemcpyHostToDevice, st));
+    const int kh[3] = {1, 3, 3}, kw[3] = {3, 1, 3}, koff[3] = {0, 3, 6};
+
+    int32_t max_sub = 0;
+    for (int32_t c = 0; c < num_segment; c++) max_sub = std::max(max_sub, seg[c + 1] - seg[c]);
+    DevBuf d_uv, d_tiles, d_mins, d_shift, d_dp, d_mvn, d_ncl;
+    CU_CHECK(ctx, d_uv.alloc(sizeof(int2) * (size_t)max_sub));
+    CU_CHECK(ctx, d_tiles.alloc(sizeof(float) * 2 * (size_t)max_sub * T * T));
+    CU_CHECK(ctx, d_mins.alloc(sizeof(float) * 2 * (size_t)max_sub));
+    CU_CHECK(ctx, d_shift.alloc(sizeof(float) * 2 * (size_t)max_sub));
+    CU_CHECK(ctx, d_dp.alloc(sizeof(float) * 16 * (size_t)max_sub * 3));
+    CU_CHECK(ctx, d_mvn.alloc(sizeof(float) * (size_t)max_sub * 16 * 5));
+    CU_CHECK(ctx, d_ncl.alloc(sizeof(int32_t) * (size_t)max_sub));
+
+    float sduv[2] = {0.0f, 0.0f};
+    int32_t num_cp_current = 0;
+    bool ok = false;
+    for (int32_t c = 0; c < num_segment; c++) {
+        const int32_t nsub = seg[c + 1] - seg[c];
+        if (nsub <= 0) continue;
+        std::vector<int2> uv(nsub);
+        for (int32_t k = 0; k < nsub; k++) {
+            const int32_t g = cand[seg[c] + k];
+            uv[k].x = (int32_t)xyuvav[6 * (size_t)g + 2];
+            uv[k].y = (int32_t)xyuvav[6 * (size_t)g + 3];
+        }
+        CU_CHECK(ctx, cudaMemcpyAsync(d_uv.p, uv.data(), sizeof(int2) * (size_t)nsub, cudaMemcpyHostToDevice, st));
+        float *tiles0 = d_tiles.as<float>(), *tiles1 = tiles0 + (size_t)nsub * T * T;
+        for (int variant = -1; variant <= 2; variant++) {
+            const int kk = variant < 0 ? 0 : variant;
+            cp_tiles_kernel<<<dim3(nsub, 2), kT, 0, st>>>(i0->d, i1->d, H, W, d_uv.as<int2>(), nsub, ocw_chip, variant,
+                                                         d_kern.as<float>() + koff[kk], kh[kk], kw[kk], tiles0, d_mins.as<float>());
+            ctx->launches++;
+            if (variant >= 0) {
+                cp_shift_scan_kernel<<<1, 32, 0, st>>>(d_mins.as<float>(), nsub, kw[kk], d_shift.as<float>());
+                cp_apply_shift_kernel<<<dim3(nsub, 2), kT, 0, st>>>(tiles0, d_shift.as<float>(), nsub, T * T);
+                ctx->launches += 2;
+            }
+            CU_CHECK(ctx, cudaGetLastError());
+            for (int c3 = 1; c3 < 3; c3++) {
+                const int ocw = p->vec_ocw[c3];
+                const int slot = (c3 - 1) * 8 + (variant + 1) * 2;
+                for (int dir = 0; dir < 2; dir++) {
+                    MatchLaunch L;
+                    L.chips = (dir ? tiles1 : tiles0) + (size_t)(ocw_chip - ocw) * T + (ocw_chip - ocw);
+                    L.chip_stride = (int64_t)T * T; L.chip_pitch = T;
+                    L.sareas = dir ? tiles0 : tiles1;
+                    L.D = T; L.P = P; L.piv = d_piv.as<int32_t>(); L.sign = 1;
+                    L.n = nsub; L.ocw = ocw; L.negate = dir ? -1.0f : 1.0f;
+                    L.dp = d_dp.as<float>() + (size_t)(slot + dir) * nsub * 3;
+                    L.max_cells = (int64_t)(T - 2 * ocw - 1) * (T - 2 * ocw - 1);
+                    L.max_sarea = (int64_t)T * T;
+                    if (int rc = launch_match(ctx, L)) return rc;
+                }
+            }
+        }
+        // clusters of the 16 attempts (:389) and the prominent ones (:394-410)
+        if (int rc = post_cluster(ctx, d_dp.as<float>(), nsub, 16, d_mvn.as<float>(), d_ncl.as<int32_t>())) return rc;
+        std::vector<float> mvn((size_t)nsub * 16 * 5);
+        std::vector<int32_t> ncl(nsub);
+        CU_CHECK(ctx, cudaMemcpyAsync(mvn.data(), d_mvn.p, sizeof(float) * mvn.size(), cudaMemcpyDeviceToHost, st));
+        CU_CHECK(ctx, cudaMemcpyAsync(ncl.data(), d_ncl.p, sizeof(int32_t) * ncl.size(), cudaMemcpyDeviceToHost, st));
+        CU_CHECK(ctx, cudaStreamSynchronize(st));
+        for (int32_t k = 0; k < nsub; k++)
+            for (int32_t q = 0; q < ncl[k]; q++) {
+                const float *row = &mvn[((size_t)k * 16 + q) * 5];
+                if ((double)row[4] >= 0.6) {
+                    sduv[0] += row[0]; sduv[1] += row[1];
+                    flag_cp[cand[seg[c] + k]] = 1;
+                    num_cp_current++;
+                }
+            }
+        if (num_cp <= num_cp_current) { ok = true; break; }
+    }
+    if (num_cp_found) *num_cp_found = num_cp_current;
+    if (!ok && num_cp_current >= p->num_cp_min) ok = true;   // :437-441
+    if (!ok) return 0;
+    const float du = sduv[0] / (float)num_cp_current, dv = sduv[1] / (float)num_cp_current;
+    offset[0] = du > 0 ? (int32_t)((double)du + 0.5) : (int32_t)((double)du - 0.5);   // :455-473
+    offset[1] = dv > 0 ? (int32_t)((double)dv + 0.5) : (int32_t)((double)dv - 0.5);
+    *result = 1;
+    return 0;
+}

@@ -34,6 +34,8 @@ struct MatchArgs {
     int sign;
     const float *chips, *sareas;
     int D, P;
+    long long chip_stride;   // explicit mode: floats between consecutive problems' chips
+    int chip_pitch;          // ... and between chip rows (chips may be windows of larger tiles)
     int n, ocw;
     float negate;
     float *dp;
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(kThreads) match_kernel(const MatchArgs a) {
         } else {
             nd.P = a.P; nd.piv = a.piv;
             nd.u0 = nd.v0 = nd.su0 = nd.sv0 = 0;
-            nd.chip_src = a.chips + (size_t)g * S * S;
+            nd.chip_src = a.chips + (size_t)g * a.chip_stride;
             nd.sa_src = a.sareas + (size_t)g * a.D * a.D;
         }
         if (nd.P <= 0) {   // undefined behaviour in the reference (MIMC_module.c:589-591)
@@ -267,9 +269,9 @@ __global__ void __launch_bounds__(kThreads) match_kernel(const MatchArgs a) {
         int inv_ref = 0, inv_sa = 0;
         for (int i = tid; i < S * S; i += kThreads) {
             float v;
-            if (nd.chip_src) v = nd.chip_src[i];
+            int r = i / S, c = i - r * S;
+            if (nd.chip_src) v = nd.chip_src[r * a.chip_pitch + c];
             else {
-                int r = i / S, c = i - r * S;
                 int iv = nd.v0 + r - ocw, iu = nd.u0 + c - ocw;   // extract_refchip :845-855 (no bounds check there)
                 v = (iu >= 0 && iu < a.W && iv >= 0 && iv < a.H) ? __ldg(&a.ref[(size_t)iv * a.W + iu]) : 0.0f;
             }
@@ -425,6 +427,8 @@ int launch_match(mimc3cu_ctx *ctx, const MatchLaunch &L) {
     a.ref = L.ref; a.srch = L.srch; a.H = L.H; a.W = L.W; a.node_uv = L.node_uv;
     a.off_u = L.off_u; a.off_v = L.off_v; a.csr_off = L.csr_off; a.piv = (const int2 *)L.piv; a.sign = L.sign;
     a.chips = L.chips; a.sareas = L.sareas; a.D = L.D; a.P = L.P;
+    a.chip_stride = L.chip_stride ? L.chip_stride : (long long)S * S;
+    a.chip_pitch = L.chip_pitch ? L.chip_pitch : S;
     a.n = L.n; a.ocw = L.ocw; a.negate = L.negate; a.dp = L.dp; a.peak = (int2 *)L.peak; a.ncell = L.ncell;
     a.node_list = L.node_list; a.list_count = L.list_count; a.list_n = L.list_n;
     a.sa_cap = (int)((smem - chip_bytes) / sizeof(float));

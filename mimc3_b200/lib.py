@@ -24,7 +24,8 @@ class Params(C.Structure):
     _fields_ = [("vec_ocw", C.c_int32 * 4), ("AW_CRE", C.c_float), ("AW_SF", C.c_float), ("mpp", C.c_float),
                 ("meter_per_spacing", C.c_float), ("radius_neighbor_dpf1", C.c_float),
                 ("radius_neighbor_ps", C.c_float), ("dt", C.c_float), ("dimx", C.c_int32), ("dimy", C.c_int32),
-                ("num_dp", C.c_int32)]
+                ("num_dp", C.c_int32), ("num_cp_max", C.c_int32), ("num_cp_min", C.c_int32),
+                ("ratio_cp", C.c_float), ("thres_spd_cp", C.c_float)]
 
 
 _lib = None
@@ -77,6 +78,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "mimc3cu_free": (C.c_int, [vp, vp]),
         "mimc3cu_memcpy_d2h": (C.c_int, [vp, vp, vp, C.c_size_t]),
         "mimc3cu_memcpy_h2d": (C.c_int, [vp, vp, vp, C.c_size_t]),
+        "mimc3cu_get_offset_image": (C.c_int, [vp, i32, i32, vp, i32, C.POINTER(Params), vp, vp, vp, C.c_uint32, vp, vp,
+                                               C.POINTER(i32), C.POINTER(i32)]),
         "mimc3cu_set_matcher": (C.c_int, [vp, i32]),
         "mimc3cu_last_matcher": (C.c_int, [vp]),
         "mimc3cu_image_class": (C.c_int, [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(f32)]),
@@ -100,6 +103,7 @@ EXPORTED_SYMBOLS = (
     "mimc3cu_postprocess_stage", "mimc3cu_finalize", "mimc3cu_fp32_peak", "mimc3cu_timing_enable",
     "mimc3cu_timing_read", "mimc3cu_malloc", "mimc3cu_free", "mimc3cu_memcpy_d2h",
     "mimc3cu_memcpy_h2d", "mimc3cu_set_matcher", "mimc3cu_last_matcher", "mimc3cu_image_class",
+    "mimc3cu_get_offset_image",
 )
 
 
@@ -280,6 +284,16 @@ class Context:
         off = np.ascontiguousarray(offset, dtype=np.int32)
         self._ck(self.L.mimc3cu_multimatch_async(self.h, i0, i1, i0c, i1c, _ptr(off), C.byref(params), _ptr(dp_dev),
                                                  _ptr(ncell_dev)))
+
+    # control points ---------------------------------------------------------------------------------
+    def get_offset_image(self, i0, i1, xyuvav, params, seed):
+        """get_offset_image (MIMC_module.c:33-492) -> (result 1/-1, offset int32[2], flag_cp uint8[n], #CP)."""
+        x = np.ascontiguousarray(xyuvav, dtype=np.float64)
+        off = np.zeros(2, np.int32); flag = np.zeros(x.shape[0], np.uint8)
+        res = C.c_int32(); ncp = C.c_int32()
+        self._ck(self.L.mimc3cu_get_offset_image(self.h, i0, i1, _ptr(x), x.shape[0], C.byref(params), None, None, None,
+                                                 int(seed) & 0xffffffff, _ptr(off), _ptr(flag), C.byref(res), C.byref(ncp)))
+        return res.value, off, flag, ncp.value
 
     # postprocess ------------------------------------------------------------------------------------
     def cluster_async(self, dp_dev, n, num_dp, mvn_dev, ncl_dev):
