@@ -9,6 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmimc3cu.so")
+DROPIN = os.path.join(HERE, "libmimc3cu_dropin.a")
 SOURCES = ["api.cu", "match.cu", "match2.cu", "sat.cu", "cp.cu", "conv2.cu", "post.cu", "probe.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOST_CXX = "/usr/bin/g++"
@@ -23,7 +24,7 @@ FLAGS = [
 
 
 def _stale() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(DROPIN):
         return True
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "mimc3cu.h"), __file__]
@@ -51,7 +52,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed on {src}")
     cmd = [NVCC, "-shared", "-o", LIB, *objs, "-ccbin", HOST_CXX, "-Xcompiler", "-pthread", "-lcudart"]
     subprocess.run(cmd, check=True)
+    build_dropin()
     return LIB
+
+
+def build_dropin() -> str:
+    """libmimc3cu_dropin.a: the reference's MIMC_module.h entry points over the C ABI (host C++).
+    Its undefined symbols (the driver's globals and GMA_*_create) resolve when the reference
+    driver is linked against it -- see INTEGRATION.md."""
+    obj = os.path.join(HERE, "build", "dropin.o")
+    subprocess.run([HOST_CXX, "-std=c++17", "-O2", "-fPIC", "-pthread", "-c", os.path.join(CSRC, "dropin.cpp"), "-o", obj], check=True)
+    if os.path.exists(DROPIN):
+        os.remove(DROPIN)
+    subprocess.run(["ar", "rcs", DROPIN, obj], check=True)
+    return DROPIN
 
 
 if __name__ == "__main__":
