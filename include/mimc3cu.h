@@ -179,9 +179,37 @@ int mimc3cu_cluster_async(mimc3cu_ctx *ctx, const float *dp_dev, int32_t n, int3
 int mimc3cu_postprocess(mimc3cu_ctx *ctx, const float *dp_dev, const double *xyuvav, const mimc3cu_params *p,
                         float *planes_dev, int32_t *stats);
 
+/* ---- postprocess of one band of node rows (multi-GPU) --------------------------------------
+ * The node grid is split into contiguous bands of rows, one per GPU/process.  Every iterative
+ * stage reads neighbours up to mimc3cu_band_halo() rows away (3 rows for get_dpf1, 5 for the
+ * pseudosmoothing with the reference's radii), so each band keeps that many halo rows of its
+ * neighbours and refreshes them after every committed sweep.  The library runs the reference's
+ * sweep control unchanged and calls back into the host for the three communication steps; the
+ * host implements them with whatever transport it has (mimc3_b200/bands.py: torch.distributed,
+ * NCCL over NVLink on GPUs).  Arrays are DEVICE pointers to the band's LOCAL arrays: local row 0 is
+ * global row max(0, own_row0 - halo); rows are dimx elements of elem_bytes bytes.
+ *   halo_exchange   overwrite my halo rows with the neighbours' current owned rows
+ *   halo_or_reduce  uint8 flags: OR my halo rows into the owners' rows (owners' rows are final after it)
+ *   allreduce_sum   int32 counters on the HOST, summed over all bands, in place
+ * Each returns 0 on success.  All bands must call mimc3cu_postprocess_band collectively. */
+typedef struct mimc3cu_band_comm {
+    void *user;
+    int (*halo_exchange)(void *user, void *const *arrays, const int32_t *elem_bytes, int32_t count);
+    int (*halo_or_reduce)(void *user, void *flags_u8);
+    int (*allreduce_sum)(void *user, int32_t *vals, int32_t count);
+} mimc3cu_band_comm;
+int mimc3cu_band_halo(const mimc3cu_params *p);
+/* dp_dev (num_dp, own_rows*dimx, 3) of the OWNED nodes; xyuvav = the GLOBAL (dimy*dimx, 6) matrix on
+ * the host; p->dimx/dimy = the GLOBAL grid; planes_dev 5 x (own_rows, dimx).  comm == NULL is only
+ * valid for the single band [0, dimy) (== mimc3cu_postprocess). stats are global. */
+int mimc3cu_postprocess_band(mimc3cu_ctx *ctx, const float *dp_dev, const double *xyuvav, const mimc3cu_params *p,
+                             int32_t own_row0, int32_t own_rows, const mimc3cu_band_comm *comm, float *planes_dev,
+                             int32_t *stats);
+
 /* Intermediate fields of the last mimc3cu_postprocess call, copied to the host for the
  * differential tests: which = 0 dpf0 (i32), 1 dpf1 ids (i32), 2 dpf1 dx (f32), 3 dpf1 dy,
- * 4 pseudosmoothing ids, 5 ps dx, 6 ps dy, 7 ncl (i32). `host` holds n 4-byte values. */
+ * 4 pseudosmoothing ids, 5 ps dx, 6 ps dy, 7 ncl (i32). `host` holds n 4-byte values
+ * (n = the owned nodes of the band in band mode). */
 int mimc3cu_postprocess_stage(mimc3cu_ctx *ctx, int32_t which, void *host);
 
 /* main()'s tail, MIMC_main.c:356-402: mean of the non-NaN du,dv removed (sequential

@@ -523,6 +523,12 @@ int mimc3cu_postprocess(mimc3cu_ctx *ctx, const float *dp_dev, const double *xyu
     ScopedTimer tm(ctx, 2);
     return post_run(ctx, dp_dev, xyuvav, p, planes_dev, stats);
 }
+int mimc3cu_band_halo(const mimc3cu_params *p) { return p ? post_band_halo(p) : 0; }
+int mimc3cu_postprocess_band(mimc3cu_ctx *ctx, const float *dp_dev, const double *xyuvav, const mimc3cu_params *p, int32_t own_row0,
+                             int32_t own_rows, const mimc3cu_band_comm *comm, float *planes_dev, int32_t *stats) {
+    ScopedTimer tm(ctx, 2);
+    return post_run_band(ctx, dp_dev, xyuvav, p, own_row0, own_rows, comm, planes_dev, stats);
+}
 int mimc3cu_postprocess_stage(mimc3cu_ctx *ctx, int32_t which, void *host) { return post_stage(ctx, which, host); }
 int mimc3cu_finalize(mimc3cu_ctx *ctx, float *planes_dev, const mimc3cu_params *p, float *du_cp, float *dv_cp) {
     return post_finalize(ctx, planes_dev, p, du_cp, dv_cp);

@@ -156,6 +156,9 @@ int launch_cast_u16(mimc3cu_ctx *ctx, const uint16_t *src, float *dst, size_t co
 int post_cluster(mimc3cu_ctx *ctx, const float *dp, int32_t n, int32_t num_dp, float *mvn, int32_t *ncl);
 int post_run(mimc3cu_ctx *ctx, const float *dp, const double *xyuvav_host, const mimc3cu_params *p, float *planes,
              int32_t *stats);
+int post_run_band(mimc3cu_ctx *ctx, const float *dp, const double *xyuvav, const mimc3cu_params *p, int32_t own_row0,
+                  int32_t own_rows, const mimc3cu_band_comm *comm, float *planes, int32_t *stats);
+int post_band_halo(const mimc3cu_params *p);
 int post_stage(mimc3cu_ctx *ctx, int32_t which, void *host);
 int post_finalize(mimc3cu_ctx *ctx, float *planes, const mimc3cu_params *p, float *du_cp, float *dv_cp);
 void post_free(mimc3cu_ctx *ctx);

@@ -26,8 +26,21 @@ constexpr int MAXNB = 128;    // neighbour offsets (29 for radius 3, 81 for radi
 inline int nblocks(size_t n) { return (int)((n + kT - 1) / kT); }
 }  // namespace
 
+// Geometry of one band of node rows.  The local arrays cover the owned rows plus `halo` rows of
+// the neighbouring bands on each side (clipped at the grid edges), so that "inside the local
+// array" == "inside the global grid" for every neighbour offset a sweep can reach.
+struct Band {
+    int dimx;          // nodes per grid row
+    int rows;          // local rows (owned + halo)
+    int own0, own1;    // owned local rows [own0, own1)
+    int grow0;         // global row index of local row 0
+    int gdimy;         // rows of the global grid
+};
+
 struct Post {
-    int32_t n = 0, K = 0, dimx = 0, dimy = 0;
+    int32_t n = 0, K = 0, dimx = 0, dimy = 0;   // n = OWNED nodes of the last run
+    int32_t own_off = 0;                        // first owned node in the local arrays
+    Band band;
     float *mvn = nullptr;       // (n, K, 5)
     int32_t *ncl = nullptr;     // (n)
     int32_t *dpf0 = nullptr;    // after get_dpf0
@@ -131,14 +144,26 @@ __global__ void __launch_bounds__(kT) dpf0_kernel(const float *__restrict__ mvn,
     dxb[g] = CUDART_NAN_F; dyb[g] = CUDART_NAN_F; noi[g] = 1.0f;
 }
 
+// Fields of the halo rows before the first exchange: "nothing known yet".
+__global__ void __launch_bounds__(kT) halo_init_kernel(int n, int *dpf0, int *id, float *dx, float *dy, float *dxb, float *dyb,
+                                                       float *noi, int *ncl, int *bid, uint8_t *m0, uint8_t *m1) {
+    int g = blockIdx.x * kT + threadIdx.x;
+    if (g >= n) return;
+    dpf0[g] = -1; id[g] = -1; ncl[g] = 0; bid[g] = -1;
+    dx[g] = CUDART_NAN_F; dy[g] = CUDART_NAN_F; dxb[g] = CUDART_NAN_F; dyb[g] = CUDART_NAN_F; noi[g] = 1.0f;
+    m0[g] = 0; m1[g] = 0;
+}
+
 // One Jacobi sweep of get_dpf1's interpolation, MIMC_module.c:1408-1566.
 __global__ void __launch_bounds__(kT) dpf1_sweep_kernel(const float *__restrict__ dx, const float *__restrict__ dy,
                                                         float *__restrict__ dxb, float *__restrict__ dyb, float *noi,
                                                         const int *__restrict__ ncl, const double *__restrict__ apv,
-                                                        const int *__restrict__ ruv, int nruv, int dimx, int dimy,
+                                                        const int *__restrict__ ruv, int nruv, const Band B,
                                                         float factor, int thres_n, float thres_weight, int *ctr) {
+    const int dimx = B.dimx, dimy = B.rows;
     int g = blockIdx.x * kT + threadIdx.x;
-    if (g >= dimx * dimy) return;
+    if (g >= dimx * (B.own1 - B.own0)) return;
+    g += B.own0 * dimx;
     if (!(isnan(__fadd_rn(dx[g], dy[g])) && ncl[g] != 0)) return;               // :1412
     const int cv = g / dimx, cu = g - cv * dimx;
     float dpe0 = __double2float_rn(__dmul_rn(apv[2 * (size_t)g], (double)factor));
@@ -209,11 +234,14 @@ __global__ void __launch_bounds__(kT) dpf1_commit_kernel(float *dx, float *dy, f
 
 // 3x3 box smoothing of the filled nodes :1623-1666 (reads dx/dy, writes dxb/dyb for interior nodes)
 __global__ void __launch_bounds__(kT) smooth_kernel(const float *dx, const float *dy, float *dxb, float *dyb,
-                                                    const int *dpf0, int dimx, int dimy) {
+                                                    const int *dpf0, const Band B) {
+    const int dimx = B.dimx;
     int g = blockIdx.x * kT + threadIdx.x;
-    if (g >= dimx * dimy) return;
+    if (g >= dimx * (B.own1 - B.own0)) return;
+    g += B.own0 * dimx;
     int cv = g / dimx, cu = g - cv * dimx;
-    if (cv < 1 || cv >= dimy - 1 || cu < 1 || cu >= dimx - 1) return;
+    const int cvg = cv + B.grow0;   // the interior test is about the GLOBAL grid
+    if (cvg < 1 || cvg >= B.gdimy - 1 || cu < 1 || cu >= dimx - 1) return;
     if (dpf0[g] < 0 && !isnan(__fadd_rn(dx[g], dy[g]))) {
         float num = 0.f, sdx = 0.f, sdy = 0.f;
         for (int dv = -1; dv <= 1; dv++)
@@ -227,12 +255,15 @@ __global__ void __launch_bounds__(kT) smooth_kernel(const float *dx, const float
 
 // copy-back of the smoothing (:1668-1675) fused with snap-to-nearest-cluster (:1680-1706)
 __global__ void __launch_bounds__(kT) snap_kernel(float *dx, float *dy, const float *dxb, const float *dyb, int *id,
-                                                  const float *mvn, const int *ncl, int K, int dimx, int dimy) {
+                                                  const float *mvn, const int *ncl, int K, const Band B) {
+    const int dimx = B.dimx;
     int g = blockIdx.x * kT + threadIdx.x;
-    if (g >= dimx * dimy) return;
+    if (g >= dimx * (B.own1 - B.own0)) return;
+    g += B.own0 * dimx;
     int cv = g / dimx, cu = g - cv * dimx;
+    const int cvg = cv + B.grow0;
     float x = dx[g], y = dy[g];
-    if (cv >= 1 && cv < dimy - 1 && cu >= 1 && cu < dimx - 1) { x = dxb[g]; y = dyb[g]; }
+    if (cvg >= 1 && cvg < B.gdimy - 1 && cu >= 1 && cu < dimx - 1) { x = dxb[g]; y = dyb[g]; }
     if (id[g] < 0 && ncl[g] != 0) {
         float best = 1E+37f; int sel = 0;
         for (int c = 0; c < ncl[g]; c++) {
@@ -290,9 +321,12 @@ __global__ void __launch_bounds__(kT) ps_sweep_kernel(const uint8_t *__restrict_
                                                       const float *__restrict__ dx, const float *__restrict__ dy,
                                                       float *bx, float *by, int *bid, const float *__restrict__ mvn,
                                                       const int *__restrict__ ncl, int K, const double *__restrict__ apv,
-                                                      const int *__restrict__ ruv, int nruv, int dimx, int dimy, int *ctr) {
+                                                      const int *__restrict__ ruv, int nruv, const Band B, int *ctr) {
+    const int dimx = B.dimx, dimy = B.rows;
     int g = blockIdx.x * kT + threadIdx.x;
-    if (g >= dimx * dimy || !mask[g]) return;
+    if (g >= dimx * (B.own1 - B.own0)) return;
+    g += B.own0 * dimx;
+    if (!mask[g]) return;
     const int cv = g / dimx, cu = g - cv * dimx;
     signed char nu[MAXNB], nv[MAXNB];
     int nn = 0;
@@ -412,7 +446,7 @@ int ruv_neighbor_host(const double *xyuvav, int dimx, int dimy, float radius, fl
 int post_alloc(mimc3cu_ctx *ctx, int32_t n, int32_t K) {
     if (!ctx->post) ctx->post = new Post();
     Post &P = *ctx->post;
-    if ((size_t)n <= P.cap_n && K == P.K) { P.n = n; return 0; }
+    if ((size_t)n <= P.cap_n && K == P.K) return 0;
     post_free(ctx);
     ctx->post = new Post();
     Post &Q = *ctx->post;
@@ -469,37 +503,76 @@ int post_cluster(mimc3cu_ctx *ctx, const float *dp, int32_t n, int32_t num_dp, f
     return 0;
 }
 
-int post_run(mimc3cu_ctx *ctx, const float *dp, const double *xyuvav, const mimc3cu_params *p, float *planes, int32_t *stats) {
+// get_ruv_neighbor works on the GLOBAL grid geometry (its window is centred on the grid centre).
+static int band_halo_rows(const mimc3cu_params *p) {
+    float r = p->radius_neighbor_dpf1 > p->radius_neighbor_ps ? p->radius_neighbor_dpf1 : p->radius_neighbor_ps;
+    int h = (int)r;
+    if ((float)h < r) h++;
+    return h < 1 ? 1 : h;
+}
+int post_band_halo(const mimc3cu_params *p) { return band_halo_rows(p); }
+
+int post_run_band(mimc3cu_ctx *ctx, const float *dp, const double *xyuvav, const mimc3cu_params *p, int32_t own_row0,
+                  int32_t own_rows, const mimc3cu_band_comm *comm, float *planes, int32_t *stats) {
     if (!p || !dp || !xyuvav || !planes) return mimc3cu_fail(ctx, "postprocess: null argument");
-    const int32_t dimx = p->dimx, dimy = p->dimy, n = dimx * dimy, K = p->num_dp;
-    if (n <= 0 || dimx < 2) return mimc3cu_fail(ctx, "postprocess: bad grid %dx%d", dimy, dimx);
+    const int32_t dimx = p->dimx, gdimy = p->dimy, K = p->num_dp;
+    if (dimx < 2 || gdimy < 1) return mimc3cu_fail(ctx, "postprocess: bad grid %dx%d", gdimy, dimx);
+    if (own_row0 < 0 || own_rows < 1 || own_row0 + own_rows > gdimy) return mimc3cu_fail(ctx, "postprocess: bad band [%d,+%d) of %d rows", own_row0, own_rows, gdimy);
+    const int halo = band_halo_rows(p);
+    if (comm && own_rows < halo && own_rows != gdimy)
+        return mimc3cu_fail(ctx, "postprocess: a band needs at least %d node rows (has %d)", halo, own_rows);
+    Band B;
+    B.dimx = dimx; B.gdimy = gdimy;
+    const int ht = comm ? std::min(halo, own_row0) : 0, hb = comm ? std::min(halo, gdimy - own_row0 - own_rows) : 0;
+    if (!comm && own_rows != gdimy) return mimc3cu_fail(ctx, "postprocess: a partial band needs a communicator");
+    B.grow0 = own_row0 - ht; B.rows = own_rows + ht + hb; B.own0 = ht; B.own1 = ht + own_rows;
+    const int32_t nl = B.rows * dimx, n = own_rows * dimx, off = B.own0 * dimx;
     CU_CHECK(ctx, cudaSetDevice(ctx->device));
-    if (int rc = post_alloc(ctx, n, K)) return rc;
+    if (int rc = post_alloc(ctx, nl, K)) return rc;
     Post &P = *ctx->post;
-    P.dimx = dimx; P.dimy = dimy;
+    P.dimx = dimx; P.dimy = gdimy; P.n = n; P.own_off = off; P.band = B;
     cudaStream_t st = ctx->stream;
-    const int nb = nblocks(n);
+    const int nb = nblocks(n), nbl = nblocks(nl);
     int32_t h_ctr[4];
 
-    // a-priori velocity columns (xyuvav[:,4:6]) to the device
+    auto exchange = [&](std::initializer_list<void *> arrays, std::initializer_list<int32_t> bytes) -> int {
+        if (!comm || (ht == 0 && hb == 0 && own_rows == gdimy)) return 0;
+        CU_CHECK(ctx, cudaStreamSynchronize(st));
+        std::vector<void *> a(arrays); std::vector<int32_t> eb(bytes);
+        if (comm->halo_exchange(comm->user, a.data(), eb.data(), (int32_t)a.size())) return mimc3cu_fail(ctx, "postprocess: halo exchange failed");
+        return 0;
+    };
+    auto allreduce = [&](int32_t *vals, int32_t count) -> int {
+        if (!comm) return 0;
+        if (comm->allreduce_sum(comm->user, vals, count)) return mimc3cu_fail(ctx, "postprocess: all-reduce failed");
+        return 0;
+    };
+
+    // a-priori velocity columns (xyuvav[:,4:6]) of the local rows to the device
     {
-        std::vector<double> apv((size_t)n * 2);
-        for (int32_t g = 0; g < n; g++) { apv[2 * (size_t)g] = xyuvav[6 * (size_t)g + 4]; apv[2 * (size_t)g + 1] = xyuvav[6 * (size_t)g + 5]; }
-        CU_CHECK(ctx, cudaMemcpyAsync(P.apv, apv.data(), sizeof(double) * 2 * (size_t)n, cudaMemcpyHostToDevice, st));
+        std::vector<double> apv((size_t)nl * 2);
+        const double *src = xyuvav + 6 * (size_t)B.grow0 * dimx;
+        for (int32_t g = 0; g < nl; g++) { apv[2 * (size_t)g] = src[6 * (size_t)g + 4]; apv[2 * (size_t)g + 1] = src[6 * (size_t)g + 5]; }
+        CU_CHECK(ctx, cudaMemcpyAsync(P.apv, apv.data(), sizeof(double) * 2 * (size_t)nl, cudaMemcpyHostToDevice, st));
         CU_CHECK(ctx, cudaStreamSynchronize(st));
     }
-    if (int rc = post_cluster(ctx, dp, n, K, P.mvn, P.ncl)) return rc;
+    halo_init_kernel<<<nbl, kT, 0, st>>>(nl, P.dpf0, P.id, P.dx, P.dy, P.dxb, P.dyb, P.noi, P.ncl, P.bid, P.mask[0], P.mask[1]);
+    if (int rc = post_cluster(ctx, dp, n, K, P.mvn + (size_t)off * K * 5, P.ncl + off)) return rc;
     CU_CHECK(ctx, cudaMemsetAsync(P.ctr, 0, 256 * sizeof(int32_t), st));
-    dpf0_kernel<<<nb, kT, 0, st>>>(P.mvn, P.ncl, n, K, P.dpf0, P.id, P.dx, P.dy, P.dxb, P.dyb, P.noi, P.ctr);
-    ctx->launches++;
+    dpf0_kernel<<<nb, kT, 0, st>>>(P.mvn + (size_t)off * K * 5, P.ncl + off, n, K, P.dpf0 + off, P.id + off, P.dx + off, P.dy + off,
+                                   P.dxb + off, P.dyb + off, P.noi + off, P.ctr);
+    ctx->launches += 2;
     CU_CHECK(ctx, cudaMemcpyAsync(h_ctr, P.ctr, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     CU_CHECK(ctx, cudaStreamSynchronize(st));
+    if (int rc = allreduce(h_ctr, 4)) return rc;
     const int32_t holes0 = h_ctr[2];
+    if (int rc = exchange({P.dx, P.dy, P.noi}, {4, 4, 4})) return rc;
 
     // ---- get_dpf1 :1330-1718 -------------------------------------------------------------
     std::vector<int32_t> ruv;
-    int nruv = ruv_neighbor_host(xyuvav, dimx, dimy, p->radius_neighbor_dpf1, p->meter_per_spacing, ruv);
+    int nruv = ruv_neighbor_host(xyuvav, dimx, gdimy, p->radius_neighbor_dpf1, p->meter_per_spacing, ruv);
     if (nruv > 32) return mimc3cu_fail(ctx, "postprocess: %d dpf1 neighbours exceed the kernel's limit of 32", nruv);
+    for (int k = 0; k < nruv; k++) if (abs(ruv[2 * k + 1]) > halo) return mimc3cu_fail(ctx, "postprocess: neighbour offset beyond the halo");
     CU_CHECK(ctx, cudaMemcpyAsync(P.ruv, ruv.data(), sizeof(int32_t) * 2 * (size_t)nruv, cudaMemcpyHostToDevice, st));
     const float factor = (float)(1.0 / 365.0 * (double)p->dt / (double)p->mpp);   // :1393
     int32_t NOI = 0, unprocessed = 1;
@@ -511,56 +584,72 @@ int post_run(mimc3cu_ctx *ctx, const float *dp, const double *xyuvav, const mimc
             while (processed != 0) {
                 NOI++;
                 CU_CHECK(ctx, cudaMemsetAsync(P.ctr, 0, 2 * sizeof(int32_t), st));
-                dpf1_sweep_kernel<<<nb, kT, 0, st>>>(P.dx, P.dy, P.dxb, P.dyb, P.noi, P.ncl, P.apv, P.ruv, nruv, dimx, dimy, factor,
+                dpf1_sweep_kernel<<<nb, kT, 0, st>>>(P.dx, P.dy, P.dxb, P.dyb, P.noi, P.ncl, P.apv, P.ruv, nruv, B, factor,
                                                      thres_n, thres_weight, P.ctr);
-                dpf1_commit_kernel<<<nb, kT, 0, st>>>(P.dx, P.dy, P.dxb, P.dyb, P.ncl, n, P.ctr);
+                dpf1_commit_kernel<<<nb, kT, 0, st>>>(P.dx + off, P.dy + off, P.dxb + off, P.dyb + off, P.ncl + off, n, P.ctr);
                 ctx->launches += 2;
                 CU_CHECK(ctx, cudaMemcpyAsync(h_ctr, P.ctr, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
                 CU_CHECK(ctx, cudaStreamSynchronize(st));
+                if (int rc = allreduce(h_ctr, 2)) return rc;
                 processed = h_ctr[0];
                 unprocessed = h_ctr[1];
+                if (processed != 0)
+                    if (int rc = exchange({P.dx, P.dy, P.noi}, {4, 4, 4})) return rc;
             }
         }
     }
-    smooth_kernel<<<nb, kT, 0, st>>>(P.dx, P.dy, P.dxb, P.dyb, P.dpf0, dimx, dimy);
-    snap_kernel<<<nb, kT, 0, st>>>(P.dx, P.dy, P.dxb, P.dyb, P.id, P.mvn, P.ncl, K, dimx, dimy);
+    smooth_kernel<<<nb, kT, 0, st>>>(P.dx, P.dy, P.dxb, P.dyb, P.dpf0, B);
+    snap_kernel<<<nb, kT, 0, st>>>(P.dx, P.dy, P.dxb, P.dyb, P.id, P.mvn, P.ncl, K, B);
     ctx->launches += 2;
-    CU_CHECK(ctx, cudaMemcpyAsync(P.id1, P.id, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
-    CU_CHECK(ctx, cudaMemcpyAsync(P.dx1, P.dx, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
-    CU_CHECK(ctx, cudaMemcpyAsync(P.dy1, P.dy, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+    CU_CHECK(ctx, cudaMemcpyAsync(P.id1, P.id, (size_t)nl * 4, cudaMemcpyDeviceToDevice, st));
+    CU_CHECK(ctx, cudaMemcpyAsync(P.dx1, P.dx, (size_t)nl * 4, cudaMemcpyDeviceToDevice, st));
+    CU_CHECK(ctx, cudaMemcpyAsync(P.dy1, P.dy, (size_t)nl * 4, cudaMemcpyDeviceToDevice, st));
+    if (int rc = exchange({P.dx, P.dy}, {4, 4})) return rc;
 
     // ---- get_dpf_pseudosmoothing :1986-2312 ---------------------------------------------------
-    nruv = ruv_neighbor_host(xyuvav, dimx, dimy, p->radius_neighbor_ps, p->meter_per_spacing, ruv);
+    nruv = ruv_neighbor_host(xyuvav, dimx, gdimy, p->radius_neighbor_ps, p->meter_per_spacing, ruv);
     if (nruv > MAXNB) return mimc3cu_fail(ctx, "postprocess: %d pseudosmoothing neighbours exceed the limit of %d", nruv, MAXNB);
+    for (int k = 0; k < nruv; k++) if (abs(ruv[2 * k + 1]) > halo) return mimc3cu_fail(ctx, "postprocess: neighbour offset beyond the halo");
     CU_CHECK(ctx, cudaMemcpyAsync(P.ruv, ruv.data(), sizeof(int32_t) * 2 * (size_t)nruv, cudaMemcpyHostToDevice, st));
     if (int rc = ensure_stack(ctx, 8)) return rc;
+    CU_CHECK(ctx, cudaMemsetAsync(P.stack, 0, (size_t)nl, st));
     // dxb/dyb double as dxy_ps_buffer
-    ps_init_kernel<<<nb, kT, 0, st>>>(P.id, P.mvn, K, n, P.mask[0], P.stack, P.dxb, P.dyb, P.bid);
+    ps_init_kernel<<<nb, kT, 0, st>>>(P.id + off, P.mvn + (size_t)off * K * 5, K, n, P.mask[0] + off, P.stack + off, P.dxb + off,
+                                      P.dyb + off, P.bid + off);
     ctx->launches++;
+    if (int rc = exchange({P.stack}, {1})) return rc;   // mask_dp_ps_initial of the halo rows (:2205)
     int32_t ps_noi = 0, nstack = 1;
     bool any = true;
     while (ps_noi <= 100 && any) {
         uint8_t *mask = P.mask[ps_noi % 2], *next = P.mask[(ps_noi + 1) % 2];
         ps_noi++;
         if (int rc = ensure_stack(ctx, nstack + 1)) return rc;
-        CU_CHECK(ctx, cudaMemsetAsync(next, 0, (size_t)n, st));
+        CU_CHECK(ctx, cudaMemsetAsync(next, 0, (size_t)nl, st));
         CU_CHECK(ctx, cudaMemsetAsync(P.ctr, 0, 128 * sizeof(int32_t), st));
         ps_sweep_kernel<<<nb, kT, 0, st>>>(mask, next, P.stack, P.id, P.dx, P.dy, P.dxb, P.dyb, P.bid, P.mvn, P.ncl, K, P.apv, P.ruv,
-                                           nruv, dimx, dimy, P.ctr);
-        ps_commit_kernel<<<nb, kT, 0, st>>>(P.dx, P.dy, P.id, P.dxb, P.dyb, P.bid, n);
-        ps_compare_kernel<<<nb, kT, 0, st>>>(P.stack, P.cap_n, next, nstack, n, P.ctr + 8, P.ctr + 1);
-        ctx->launches += 3;
+                                           nruv, B, P.ctr);
+        ps_commit_kernel<<<nb, kT, 0, st>>>(P.dx + off, P.dy + off, P.id + off, P.dxb + off, P.dyb + off, P.bid + off, n);
+        ctx->launches += 2;
+        if (comm && (ht || hb)) {   // dirty flags scattered into the neighbours' rows: OR them into their owners
+            CU_CHECK(ctx, cudaStreamSynchronize(st));
+            if (comm->halo_or_reduce(comm->user, next)) return mimc3cu_fail(ctx, "postprocess: halo OR-reduce failed");
+        }
+        ps_compare_kernel<<<nb, kT, 0, st>>>(P.stack + off, P.cap_n, next + off, nstack, n, P.ctr + 8, P.ctr + 1);
+        ctx->launches++;
         int32_t h[128];
         CU_CHECK(ctx, cudaMemcpyAsync(h, P.ctr, 128 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         CU_CHECK(ctx, cudaStreamSynchronize(st));
+        if (int rc = allreduce(h, 128)) return rc;
         any = h[0] != 0;
         bool fluct = false;
         for (int k = nstack - 1; k >= 0; k--) if (h[8 + k] == 0) { fluct = true; break; }
         if (fluct) { ps_noi--; break; }
-        CU_CHECK(ctx, cudaMemcpyAsync(P.stack + (size_t)nstack * P.cap_n, next, (size_t)n, cudaMemcpyDeviceToDevice, st));
+        CU_CHECK(ctx, cudaMemcpyAsync(P.stack + (size_t)nstack * P.cap_n, next, (size_t)nl, cudaMemcpyDeviceToDevice, st));
         nstack++;
+        if (any)
+            if (int rc = exchange({P.dx, P.dy}, {4, 4})) return rc;
     }
-    pack_kernel<<<nb, kT, 0, st>>>(P.id, P.mvn, K, n, planes);
+    pack_kernel<<<nb, kT, 0, st>>>(P.id + off, P.mvn + (size_t)off * K * 5, K, n, planes);
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     CU_CHECK(ctx, cudaStreamSynchronize(st));
@@ -568,19 +657,25 @@ int post_run(mimc3cu_ctx *ctx, const float *dp, const double *xyuvav, const mimc
     return 0;
 }
 
+int post_run(mimc3cu_ctx *ctx, const float *dp, const double *xyuvav, const mimc3cu_params *p, float *planes, int32_t *stats) {
+    if (!p) return mimc3cu_fail(ctx, "postprocess: null argument");
+    return post_run_band(ctx, dp, xyuvav, p, 0, p->dimy, nullptr, planes, stats);
+}
+
 int post_stage(mimc3cu_ctx *ctx, int32_t which, void *host) {
     if (!ctx->post || ctx->post->n == 0) return mimc3cu_fail(ctx, "postprocess_stage: no postprocess run yet");
     Post &P = *ctx->post;
     const void *src = nullptr;
+    const size_t off = (size_t)P.own_off;
     switch (which) {
-        case 0: src = P.dpf0; break;
-        case 1: src = P.id1; break;
-        case 2: src = P.dx1; break;
-        case 3: src = P.dy1; break;
-        case 4: src = P.id; break;
-        case 5: src = P.dx; break;
-        case 6: src = P.dy; break;
-        case 7: src = P.ncl; break;
+        case 0: src = P.dpf0 + off; break;
+        case 1: src = P.id1 + off; break;
+        case 2: src = P.dx1 + off; break;
+        case 3: src = P.dy1 + off; break;
+        case 4: src = P.id + off; break;
+        case 5: src = P.dx + off; break;
+        case 6: src = P.dy + off; break;
+        case 7: src = P.ncl + off; break;
         default: return mimc3cu_fail(ctx, "postprocess_stage: unknown field %d", which);
     }
     CU_CHECK(ctx, cudaMemcpyAsync(host, src, (size_t)P.n * 4, cudaMemcpyDeviceToHost, ctx->stream));

@@ -80,6 +80,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "mimc3cu_memcpy_h2d": (C.c_int, [vp, vp, vp, C.c_size_t]),
         "mimc3cu_get_offset_image": (C.c_int, [vp, i32, i32, vp, i32, C.POINTER(Params), vp, vp, vp, C.c_uint32, vp, vp,
                                                C.POINTER(i32), C.POINTER(i32)]),
+        "mimc3cu_band_halo": (C.c_int, [C.POINTER(Params)]),
+        "mimc3cu_postprocess_band": (C.c_int, [vp, vp, vp, C.POINTER(Params), i32, i32, vp, vp, vp]),
         "mimc3cu_set_matcher": (C.c_int, [vp, i32]),
         "mimc3cu_last_matcher": (C.c_int, [vp]),
         "mimc3cu_image_class": (C.c_int, [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(f32)]),
@@ -103,7 +105,7 @@ EXPORTED_SYMBOLS = (
     "mimc3cu_postprocess_stage", "mimc3cu_finalize", "mimc3cu_fp32_peak", "mimc3cu_timing_enable",
     "mimc3cu_timing_read", "mimc3cu_malloc", "mimc3cu_free", "mimc3cu_memcpy_d2h",
     "mimc3cu_memcpy_h2d", "mimc3cu_set_matcher", "mimc3cu_last_matcher", "mimc3cu_image_class",
-    "mimc3cu_get_offset_image",
+    "mimc3cu_get_offset_image", "mimc3cu_band_halo", "mimc3cu_postprocess_band",
 )
 
 
@@ -136,6 +138,11 @@ def params_for(xyuvav: np.ndarray, dimx: int, dimy: int, dt: float) -> Params:
     p.dt = np.float32(dt)
     p.dimx, p.dimy = dimx, dimy
     return p
+
+
+def band_halo(params) -> int:
+    """Node rows of halo each band keeps of its neighbours (mimc3cu_band_halo)."""
+    return int(load_library().mimc3cu_band_halo(C.byref(params)))
 
 
 def get_uv_pivot(xyuvav, dt, mpp, ocw, H, W, aw_sf=1.8, aw_cre=10.0):
@@ -303,6 +310,19 @@ class Context:
         x = np.ascontiguousarray(xyuvav, dtype=np.float64)
         stats = np.zeros(4, np.int32)
         self._ck(self.L.mimc3cu_postprocess(self.h, _ptr(dp_dev), _ptr(x), C.byref(params), _ptr(planes_dev), _ptr(stats)))
+        return stats
+
+    def postprocess_band(self, dp_dev, xyuvav_global, params_global, own_row0, own_rows, comm, planes_dev):
+        """One band of node rows of mimc2_postprocess (collective over the bands).  ``comm`` is a
+        bands.BandComm (or None for the single band [0, dimy))."""
+        x = np.ascontiguousarray(xyuvav_global, dtype=np.float64)
+        stats = np.zeros(4, np.int32)
+        cptr = C.cast(C.pointer(comm.struct), C.c_void_p) if comm is not None else None
+        rc = self.L.mimc3cu_postprocess_band(self.h, _ptr(dp_dev), _ptr(x), C.byref(params_global), own_row0, own_rows, cptr,
+                                             _ptr(planes_dev), _ptr(stats))
+        if rc and comm is not None and comm.error is not None:
+            raise comm.error
+        self._ck(rc)
         return stats
 
     def postprocess_stage(self, which, n):

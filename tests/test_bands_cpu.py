@@ -1,0 +1,126 @@
+"""CPU tests of the N > 1 host logic (mimc3_b200/bands.py): band partition, halo exchange,
+OR-reduction of scattered flags and the counter all-reduce, over gloo with world_size 2 and 3
+(one process per rank, 127.0.0.1 rendezvous) and over the in-process thread transport."""
+import os
+import socket
+import threading
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from mimc3_b200 import bands
+
+
+def test_split_rows_covers_and_balances():
+    for dimy, world in ((813, 8), (100, 2), (40, 8), (17, 3)):
+        parts = bands.split_rows(dimy, world, min_rows=5)
+        assert parts[0][0] == 0 and sum(r for _, r in parts) == dimy
+        assert all(parts[k][0] + parts[k][1] == parts[k + 1][0] for k in range(world - 1))
+        assert min(r for _, r in parts) >= 5
+    w = np.ones(100); w[40:60] = 10.0                   # fast-glacier rows are 10x dearer
+    parts = bands.split_rows(100, 4, min_rows=5, weights=w)
+    loads = [w[a:a + r].sum() for a, r in parts]
+    assert max(loads) / (sum(loads) / 4) < 1.35
+    with pytest.raises(ValueError):
+        bands.split_rows(9, 2, min_rows=5)
+
+
+def _global_fields(gdimy, dimx, seed=0):
+    rng = np.random.default_rng(seed)
+    f32 = rng.normal(size=(gdimy, dimx)).astype(np.float32)
+    i32 = rng.integers(-5, 50, size=(gdimy, dimx)).astype(np.int32)
+    u8 = (rng.random((gdimy, dimx)) < 0.3).astype(np.uint8)
+    return f32, i32, u8
+
+
+def _rank_body(transport, rank, world, gdimy, dimx, halo, parts):
+    """What every rank checks; returns a list of failure strings."""
+    fails = []
+    f32, i32, u8 = _global_fields(gdimy, dimx)
+    row0, rows = parts[rank]
+    geo = bands.BandGeometry(dimx, gdimy, row0, rows, halo)
+    lo = row0 - geo.ht
+
+    def local(a):   # owned rows right, halo rows poisoned
+        t = torch.from_numpy(a[lo:lo + geo.rows].copy())
+        poison = torch.full_like(t, 77)
+        poison[geo.own0:geo.own0 + rows] = t[geo.own0:geo.own0 + rows]
+        return poison
+    lf, li, lu = local(f32), local(i32), local(u8)
+    views = [lf.view(torch.uint8).view(geo.rows, dimx * 4), li.view(torch.uint8).view(geo.rows, dimx * 4), lu.view(geo.rows, dimx)]
+    bands.halo_exchange(transport, geo, views)
+    for name, got, want in (("f32", lf, f32), ("i32", li, i32), ("u8", lu, u8)):
+        if not np.array_equal(got.numpy(), want[lo:lo + geo.rows]):
+            fails.append(f"rank {rank}: halo rows of {name} wrong after the exchange")
+    # scatter: every rank marks flags in its whole local array; after the OR-reduce the owned rows
+    # must equal the OR over all ranks that can see them
+    rng = np.random.default_rng(100 + rank)
+    mine = (rng.random((geo.rows, dimx)) < 0.2).astype(np.uint8)
+    want = np.zeros((gdimy, dimx), np.uint8)
+    for r in range(world):
+        g2 = bands.BandGeometry(dimx, gdimy, parts[r][0], parts[r][1], halo)
+        m2 = (np.random.default_rng(100 + r).random((g2.rows, dimx)) < 0.2).astype(np.uint8)
+        l2 = parts[r][0] - g2.ht
+        want[l2:l2 + g2.rows] |= m2
+    t = torch.from_numpy(mine.copy())
+    bands.halo_or_reduce(transport, geo, t)
+    if not np.array_equal(t.numpy()[geo.own0:geo.own0 + rows], want[row0:row0 + rows]):
+        fails.append(f"rank {rank}: OR-reduce of scattered flags wrong")
+    c = torch.tensor([rank + 1, 10 * (rank + 1), 0], dtype=torch.int32)
+    transport.allreduce_sum(c)
+    s = world * (world + 1) // 2
+    if c.tolist() != [s, 10 * s, 0]:
+        fails.append(f"rank {rank}: all-reduce gave {c.tolist()}")
+    return fails
+
+
+def _gloo_worker(rank, world, port, gdimy, dimx, halo, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        parts = bands.split_rows(gdimy, world, min_rows=halo)
+        q.put(_rank_body(bands.DistTransport(), rank, world, gdimy, dimx, halo, parts))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("world", (2, 3))
+def test_halo_exchange_over_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, 37, 11, 5, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    fails = []
+    for _ in procs:
+        fails += q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert not fails, fails
+
+
+def test_halo_exchange_over_threads():
+    world, gdimy, dimx, halo = 4, 41, 7, 5
+    shared = bands.ThreadTransport.Shared(world)
+    parts = bands.split_rows(gdimy, world, min_rows=halo)
+    out = [None] * world
+
+    def run(r):
+        out[r] = _rank_body(bands.ThreadTransport(shared, r), r, world, gdimy, dimx, halo, parts)
+    th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=60)
+    assert all(o == [] for o in out), out
