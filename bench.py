@@ -23,9 +23,10 @@ one pass of that path over every node of the workload.
                 threads) on a bounded node sample of the same workload.
 
 N > 1 (torchrun): weak scaling.  Every rank owns one tile of a vertical mosaic (its own
-image pair + node-row band), matches it with no data-path collective, then dp is gathered
-over NCCL to rank 0, which postprocesses the whole mosaic grid (cross-band neighbourhoods
-included).  Timing = max over ranks.
+image pair + node-row band) and matches it with no data-path collective.  The postprocess
+runs banded over the whole mosaic grid: each rank sweeps its own band and exchanges halo
+rows / dirty flags / sweep counters with its neighbours over NCCL (mimc3_b200/bands.py),
+then the five planes are gathered on rank 0.  Timing = max over ranks.
 """
 from __future__ import annotations
 
@@ -280,18 +281,19 @@ def main():
     del sc.i0, sc.i1
     torch.cuda.empty_cache()
 
-    # global (mosaic) grid for N > 1: bands stacked along y, postprocessed on rank 0
+    # global (mosaic) grid for N > 1: the ranks' grids stacked along y = the bands of one grid
     if world > 1:
+        from mimc3_b200 import bands
         gl_dimy = sc.dimy * world
         xy_all = [None] * world
         dist.all_gather_object(xy_all, sc.xyuvav)
-        if rank == 0:
-            xy_glob = np.concatenate(xy_all, axis=0)
-            # make map-y continue down the mosaic so the global grid is regular
-            for r in range(world):
-                xy_glob[r * n:(r + 1) * n, 1] -= r * sc.dimy * sc.spacing * sc.mpp
-            gparams = lib.params_for(xy_glob, sc.dimx, gl_dimy, sc.dt)
-            dp_glob = torch.empty((32, n * world, 3), dtype=torch.float32, device=dev)
+        xy_glob = np.concatenate(xy_all, axis=0)
+        # make map-y continue down the mosaic so the global grid is regular
+        for r in range(world):
+            xy_glob[r * n:(r + 1) * n, 1] -= r * sc.dimy * sc.spacing * sc.mpp
+        gparams = lib.params_for(xy_glob, sc.dimx, gl_dimy, sc.dt)
+        transport = bands.DistTransport()
+        comm_stats = {"halo_exchanges": 0, "allreduces": 0}
 
     dp = torch.empty((32, n, 3), dtype=torch.float32, device=dev)
     ncell = torch.empty((32, n), dtype=torch.int32, device=dev)
@@ -303,16 +305,14 @@ def main():
         ctx.multimatch_async(hd["i0"], hd["i1"], hd["i0c"], hd["i1c"], offset, params, dp, ncell if collect_ncell else None)
         if world == 1:
             return ctx.postprocess(dp, sc.xyuvav, params, planes)
-        # gather the bands' dp on rank 0 (NCCL over NVLink), then postprocess the mosaic grid
-        ctx.sync()
-        parts = [torch.empty_like(dp) for _ in range(world)] if rank == 0 else None
-        dist.gather(dp, parts, dst=0)
-        if rank == 0:
-            for r in range(world):
-                dp_glob[:, r * n:(r + 1) * n].copy_(parts[r])
-            torch.cuda.current_stream().synchronize()
-            return ctx.postprocess(dp_glob, xy_glob, gparams, planes)
-        return None
+        # banded postprocess: halo exchange + counter all-reduce per sweep over NCCL, then the final gather
+        band_planes, st, comm = pl.postprocess_band(dp, xy_glob, gparams, rank * sc.dimy, sc.dimy, transport)
+        comm_stats["halo_exchanges"] += comm.n_exchanges; comm_stats["allreduces"] += comm.n_allreduce
+        with torch.cuda.stream(stream):
+            parts = transport.gather_rows(band_planes, dst=0)
+            if rank == 0:
+                torch.cat(parts, dim=1, out=planes)
+        return st
 
     def barrier():
         ctx.sync()
@@ -427,6 +427,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32 products, f64 accumulation (bit-exact vs the reference)", "data": "synthetic", "config": config,
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "collectives": (dict(comm_stats, backend="nccl", pattern="neighbour halo rows + int32 counter all-reduce per sweep, final gather of 5 planes") if world > 1 else None),
                 "postprocess_stats": {"dpf1_sweeps": int(stats[0]), "pseudosmoothing_sweeps": int(stats[1]), "holes_after_dpf0": int(stats[2])} if stats is not None else None}
         print(json.dumps(line), flush=True)
     pl.close()

@@ -74,6 +74,17 @@ class Pipeline:
         stats = self.ctx.postprocess(dp, self.xyuvav, self.params, planes)
         return planes, stats
 
+    def postprocess_band(self, dp, xyuvav_global, params_global, own_row0, own_rows, transport):
+        """This rank's band of the postprocess; collective over all ranks of ``transport``
+        (halo exchange + counter all-reduce per sweep, see bands.py).  Returns (planes (5, own_rows,
+        dimx) on the device, stats, BandComm)."""
+        from . import bands
+        geo = bands.BandGeometry(params_global.dimx, params_global.dimy, own_row0, own_rows, lib.band_halo(params_global))
+        comm = bands.BandComm(transport, geo, self.device, stream=self.stream)
+        planes = torch.empty((5, own_rows, params_global.dimx), dtype=torch.float32, device=self.device)
+        stats = self.ctx.postprocess_band(dp, xyuvav_global, params_global, own_row0, own_rows, comm, planes)
+        return planes, stats, comm
+
     def run(self, i0, i1, xyuvav, dimx, dimy, dt, offset, finalize=True):
         """End to end from host buffers to the five host planes (+ CP sub-pixel bias)."""
         self.set_images(i0, i1)
