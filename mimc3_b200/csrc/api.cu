@@ -176,7 +176,6 @@ void mimc3cu_destroy(mimc3cu_ctx *ctx) {
     if (ctx->statbuf) cudaFree(ctx->statbuf);
     if (ctx->overflow_list) cudaFree(ctx->overflow_list);
     if (ctx->node_uv) cudaFree(ctx->node_uv);
-    if (ctx->xyuvav_d) cudaFree(ctx->xyuvav_d);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->counter) cudaFree(ctx->counter);
     if (ctx->minbuf) cudaFree(ctx->minbuf);
@@ -306,17 +305,19 @@ int mimc3cu_set_nodes(mimc3cu_ctx *ctx, const double *xyuvav, int32_t n) {
     if (n <= 0) return mimc3cu_fail(ctx, "set_nodes: n must be positive");
     CU_CHECK(ctx, cudaSetDevice(ctx->device));
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ctx->node_uv) { CU_CHECK(ctx, cudaFree(ctx->node_uv)); ctx->node_uv = nullptr; }
-    if (ctx->xyuvav_d) { CU_CHECK(ctx, cudaFree(ctx->xyuvav_d)); ctx->xyuvav_d = nullptr; }
-    std::vector<int2> uv((size_t)n);
-    for (int32_t g = 0; g < n; g++) {
-        uv[g].x = (int32_t)xyuvav[6 * (size_t)g + 2];   // truncation, MIMC_module.c:822-823
-        uv[g].y = (int32_t)xyuvav[6 * (size_t)g + 3];
+    if ((size_t)n > ctx->node_cap) {   // device arrays are kept and reused: cudaFree/cudaMalloc churn costs more than the copies
+        if (ctx->node_uv) { CU_CHECK(ctx, cudaFree(ctx->node_uv)); ctx->node_uv = nullptr; }
+        CU_CHECK(ctx, cudaMalloc(&ctx->node_uv, sizeof(int2) * (size_t)n));
+        ctx->node_cap = (size_t)n;
     }
-    CU_CHECK(ctx, cudaMalloc(&ctx->node_uv, sizeof(int2) * (size_t)n));
+    std::vector<int2> uv((size_t)n);
+    parallel_for(n, [&](int32_t b, int32_t e) {
+        for (int32_t g = b; g < e; g++) {
+            uv[g].x = (int32_t)xyuvav[6 * (size_t)g + 2];   // truncation, MIMC_module.c:822-823
+            uv[g].y = (int32_t)xyuvav[6 * (size_t)g + 3];
+        }
+    });
     CU_CHECK(ctx, cudaMemcpy(ctx->node_uv, uv.data(), sizeof(int2) * (size_t)n, cudaMemcpyHostToDevice));
-    CU_CHECK(ctx, cudaMalloc(&ctx->xyuvav_d, sizeof(double) * 6 * (size_t)n));
-    CU_CHECK(ctx, cudaMemcpy(ctx->xyuvav_d, xyuvav, sizeof(double) * 6 * (size_t)n, cudaMemcpyHostToDevice));
     ctx->n = n;
     return 0;
 }
@@ -327,24 +328,35 @@ int mimc3cu_set_pivots(mimc3cu_ctx *ctx, int32_t slot, const int32_t *off, const
     CU_CHECK(ctx, cudaSetDevice(ctx->device));
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     PivotSet &ps = ctx->pivots[slot];
-    for (auto &b : ps.bins) { if (b.lists) { CU_CHECK(ctx, cudaFree(b.lists)); b.lists = nullptr; } b.ocw = -1; }
-    if (ps.off) { CU_CHECK(ctx, cudaFree(ps.off)); ps.off = nullptr; }
-    if (ps.piv) { CU_CHECK(ctx, cudaFree(ps.piv)); ps.piv = nullptr; }
+    for (auto &b : ps.bins) b.ocw = -1;   // node lists are rebuilt lazily (their device buffers are reused)
     ps.n = n; ps.total = off[n];
-    ps.max_abs_u = 0; ps.max_abs_v = 0; ps.max_cells = 16; ps.max_sarea_extra = 0;
     ps.last_u.assign((size_t)n, 0); ps.last_v.assign((size_t)n, 0);
+    parallel_for(n, [&](int32_t b, int32_t e) {
+        for (int32_t g = b; g < e; g++) {
+            const int32_t P = off[g + 1] - off[g];
+            if (P <= 0) continue;
+            ps.last_u[g] = abs(piv[2 * ((size_t)off[g] + P - 1)]);
+            ps.last_v[g] = abs(piv[2 * ((size_t)off[g] + P - 1) + 1]);
+        }
+    });
+    ps.max_abs_u = 0; ps.max_abs_v = 0; ps.max_cells = 16; ps.max_sarea_extra = 0;
     for (int32_t g = 0; g < n; g++) {
-        int32_t P = off[g + 1] - off[g];
-        if (P <= 0) continue;
-        int32_t lu = abs(piv[2 * ((size_t)off[g] + P - 1)]), lv = abs(piv[2 * ((size_t)off[g] + P - 1) + 1]);
-        ps.last_u[g] = lu; ps.last_v[g] = lv;
+        const int32_t lu = ps.last_u[g], lv = ps.last_v[g];
         ps.max_abs_u = std::max(ps.max_abs_u, lu); ps.max_abs_v = std::max(ps.max_abs_v, lv);
         ps.max_cells = std::max<int64_t>(ps.max_cells, (int64_t)(2 * lu + 4) * (2 * lv + 4));
     }
-    CU_CHECK(ctx, cudaMalloc(&ps.off, sizeof(int32_t) * ((size_t)n + 1)));
+    if ((size_t)n + 1 > ps.off_cap) {
+        if (ps.off) { CU_CHECK(ctx, cudaFree(ps.off)); ps.off = nullptr; }
+        CU_CHECK(ctx, cudaMalloc(&ps.off, sizeof(int32_t) * ((size_t)n + 1)));
+        ps.off_cap = (size_t)n + 1;
+    }
+    const size_t tot = (size_t)std::max<int64_t>(ps.total, 1);
+    if (tot > ps.piv_cap) {
+        if (ps.piv) { CU_CHECK(ctx, cudaFree(ps.piv)); ps.piv = nullptr; }
+        CU_CHECK(ctx, cudaMalloc(&ps.piv, sizeof(int32_t) * 2 * (tot + tot / 8)));
+        ps.piv_cap = tot + tot / 8;
+    }
     CU_CHECK(ctx, cudaMemcpy(ps.off, off, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyHostToDevice));
-    size_t tot = (size_t)std::max<int64_t>(ps.total, 1);
-    CU_CHECK(ctx, cudaMalloc(&ps.piv, sizeof(int32_t) * 2 * tot));
     if (ps.total > 0) CU_CHECK(ctx, cudaMemcpy(ps.piv, piv, sizeof(int32_t) * 2 * (size_t)ps.total, cudaMemcpyHostToDevice));
     return 0;
 }

@@ -29,6 +29,7 @@ struct PivotSet {
     int32_t *piv = nullptr;    // device, total*2
     int32_t n = 0;
     int64_t total = 0;
+    size_t off_cap = 0, piv_cap = 0;        // device capacities (elements), reused across set_pivots calls
     int32_t max_abs_u = 0, max_abs_v = 0;   // over the last pivot of every node
     int64_t max_cells = 0;                  // max (2|ul|+4)(2|vl|+4): reachable cmap region
     int64_t max_sarea_extra = 0;            // helper: max over nodes of (|ul|+2, |vl|+2) product terms
@@ -37,9 +38,10 @@ struct PivotSet {
     struct Bins {
         int32_t ocw = -1;
         int32_t *lists = nullptr;            // device: concatenated node indices
+        size_t lists_cap = 0;
         int32_t count[4] = {0, 0, 0, 0};     // [0..2] v2 bins (3/2/1 CTAs per SM), [3] general kernel
         int32_t start[4] = {0, 0, 0, 0};
-        int64_t sa_cap[3] = {0, 0, 0}, cell_cap[3] = {0, 0, 0};
+        int64_t grp_bytes[3] = {0, 0, 0};    // shared memory per node group in each v2 bin
     } bins[2];
 };
 
@@ -56,7 +58,7 @@ struct mimc3cu_ctx {
     // nodes
     int32_t n = 0;
     int2 *node_uv = nullptr;     // device (n)
-    double *xyuvav_d = nullptr;  // device (n,6)
+    size_t node_cap = 0;
 
     PivotSet pivots[MIMC3CU_MAX_PIVOT_SLOTS];
 

@@ -58,7 +58,7 @@ struct Match2Args {
     unsigned int *counter;          // dynamic node fetch for this launch
     int *overflow_list;             // nodes that do not fit this launch's shared memory
     unsigned int *overflow_count;
-    int sa_cap, cell_cap;           // per group: floats for the search area, cells of the cmap
+    int grp_bytes;                  // shared memory per group: search area + cmap values + cmap flags
     float A0, Mlo;                  // accumulator biases
     unsigned int A0_bits, Mlo_bits;
     double hi_unit, lo_unit;
@@ -69,6 +69,11 @@ struct Sums {
     double sx, sy, sxx, syy, sxy;
     int n;
 };
+
+// Resident CTAs per SM each instantiation is compiled for (register cap = 65536 / (256 * n)) and
+// that the first shared-memory bin is sized for: ocw 40 keeps 27 chip pixels per thread (80
+// registers, 3 CTAs), ocw 30 keeps 16 (64 registers, 4 CTAs); measured on B200 (profiles/).
+constexpr int min_ctas(int ocw) { return ocw == 40 ? 3 : (ocw == 15 ? 2 : 4); }
 
 template <int OCW, int G>
 struct Cfg {
@@ -153,7 +158,7 @@ struct Ctl {
 };
 
 template <int OCW, int G>
-__global__ void __launch_bounds__(kThreads, (G == 256 ? 3 : 2)) match2_kernel(const Match2Args a) {
+__global__ void __launch_bounds__(kThreads, min_ctas(OCW)) match2_kernel(const Match2Args a) {
     using C = Cfg<OCW, G>;
     constexpr int S = C::S, L = C::L;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -164,11 +169,8 @@ __global__ void __launch_bounds__(kThreads, (G == 256 ? 3 : 2)) match2_kernel(co
     const int lane = tid & 31, gwarp = t >> 5;
     Ctl<C::NWARPS> &ctl = ctl_all[grp];
 
-    // dynamic shared memory, per group: sa[sa_cap] floats | cval[cell_cap] floats | cflag[cell_cap] bytes
-    const size_t grp_bytes = (size_t)a.sa_cap * 4 + (size_t)a.cell_cap * 5;
-    float *sa = (float *)(smem_raw + grp * ((grp_bytes + 15) & ~(size_t)15));
-    float *cval = sa + a.sa_cap;
-    unsigned char *cflag = (unsigned char *)(cval + a.cell_cap);
+    // dynamic shared memory, per group and per node: sa[Dy2*pitch] floats | cval[cells] floats | cflag[cells] bytes
+    float *sa = (float *)(smem_raw + (size_t)grp * a.grp_bytes);
 
     // this thread's chip slice: row r, columns [col0, col0+len)
     const int seg = t / S, r = t - seg * S;
@@ -203,10 +205,13 @@ __global__ void __launch_bounds__(kThreads, (G == 256 ? 3 : 2)) match2_kernel(co
         const int Dx2 = 2 * dx2 + 1, Dy2 = 2 * dy2 + 1;
         const int cw = Dx2 - 2 * OCW - 1, ch = Dy2 - 2 * OCW - 1;   // cells whose 3x3 probe can be requested
         const int pitch = (Dx2 + 3) | 1;
-        if (Dy2 * pitch > a.sa_cap || cw * ch > a.cell_cap) {
+        const int sa_elems = (Dy2 * pitch + 3) & ~3, cell_elems = (cw * ch + 15) & ~15;
+        if (sa_elems * 4 + cell_elems * 5 > a.grp_bytes) {
             if (t == 0) a.overflow_list[atomicAdd(a.overflow_count, 1u)] = g;
             continue;
         }
+        float *cval = sa + sa_elems;
+        unsigned char *cflag = (unsigned char *)(cval + cell_elems);
 
         // ---- stage the chip through shared memory into registers (extract_refchip :845-855) ----
         for (int i = t; i < S * S; i += G) {
@@ -543,7 +548,7 @@ int launch_one(mimc3cu_ctx *ctx, Match2Args &a, int per_sm_target, size_t smem, 
 
 inline int group_size(int ocw) { return ocw >= 30 ? 256 : 32; }
 // resident CTAs per SM that bin k is sized for
-inline int bin_ctas(int G, int k) { return G == 256 ? 3 - k : (k == 0 ? 4 : (k == 1 ? 2 : 1)); }
+inline int bin_ctas(int ocw, int k) { return k == 0 ? (ocw == 40 ? 3 : 4) : (k == 1 ? 2 : 1); }
 
 }  // namespace
 
@@ -563,30 +568,33 @@ static void build_bins(mimc3cu_ctx *ctx, PivotSet *ps, PivotSet::Bins &B, int oc
     const int G = group_size(ocw), ngroups = kThreads / G;
     const size_t usable = ctx->smem_optin;
     for (int k = 0; k < 3; k++) {
-        const int ctas = bin_ctas(G, k);
+        const int ctas = bin_ctas(ocw, k);
         size_t per_cta = (228 * 1024 - ctas * 1024) / ctas;          // 1 KB reserved per resident CTA
         per_cta = std::min(per_cta, usable) - 4608;                  // static control blocks
         const size_t per_group = (per_cta / ngroups) & ~(size_t)15;
-        // split: cells get 1/8 of the bytes (5 B each), the search area the rest
-        B.cell_cap[k] = (int64_t)((per_group / 8) / 5) & ~15LL;
-        B.sa_cap[k] = (int64_t)((per_group - B.cell_cap[k] * 5) / 4) & ~3LL;
+        B.grp_bytes[k] = (int64_t)per_group;
     }
-    std::vector<int32_t> lists[4];
+    // two passes (count, then fill) over the host copy of the last pivots
+    std::vector<uint8_t> which((size_t)ps->n);
+    int64_t cnt[4] = {0, 0, 0, 0};
     for (int32_t g = 0; g < ps->n; g++) {
         const int64_t Dx2 = 2 * (ps->last_u[g] + ocw + 2) + 1, Dy2 = 2 * (ps->last_v[g] + ocw + 2) + 1;
-        const int64_t pitch = (Dx2 + 3) | 1, need_sa = Dy2 * pitch, need_cells = (Dx2 - 2 * ocw - 1) * (Dy2 - 2 * ocw - 1);
+        const int64_t pitch = (Dx2 + 3) | 1, need_sa = (Dy2 * pitch + 3) & ~3LL;
+        const int64_t need_cells = ((Dx2 - 2 * ocw - 1) * (Dy2 - 2 * ocw - 1) + 15) & ~15LL;
+        const int64_t need = need_sa * 4 + need_cells * 5;   // same formula as the kernel's fit test
         int k = 0;
-        while (k < 3 && (need_sa > B.sa_cap[k] || need_cells > B.cell_cap[k])) k++;
-        lists[k].push_back(g);
+        while (k < 3 && need > B.grp_bytes[k]) k++;
+        which[g] = (uint8_t)k; cnt[k]++;
     }
-    std::vector<int32_t> all;
-    for (int k = 0; k < 4; k++) {
-        B.start[k] = (int32_t)all.size();
-        B.count[k] = (int32_t)lists[k].size();
-        all.insert(all.end(), lists[k].begin(), lists[k].end());
+    std::vector<int32_t> all((size_t)ps->n);
+    int64_t pos[4];
+    for (int k = 0, acc = 0; k < 4; k++) { B.start[k] = acc; B.count[k] = (int32_t)cnt[k]; pos[k] = acc; acc += (int)cnt[k]; }
+    for (int32_t g = 0; g < ps->n; g++) all[(size_t)pos[which[g]]++] = g;
+    if ((size_t)ps->n > B.lists_cap) {
+        if (B.lists) cudaFree(B.lists);
+        cudaMalloc(&B.lists, sizeof(int32_t) * (size_t)ps->n);
+        B.lists_cap = (size_t)ps->n;
     }
-    if (B.lists) cudaFree(B.lists);
-    cudaMalloc(&B.lists, sizeof(int32_t) * std::max<size_t>(all.size(), 1));
     cudaMemcpy(B.lists, all.data(), sizeof(int32_t) * all.size(), cudaMemcpyHostToDevice);
     B.ocw = ocw;
 }
@@ -641,9 +649,8 @@ int launch_match2(mimc3cu_ctx *ctx, const MatchLaunch &L, const Image *ref, cons
         if (B->count[k] == 0) continue;
         a.node_list = B->lists + B->start[k]; a.n_list = B->count[k];
         a.counter = ctx->counter + 1 + k;
-        a.sa_cap = (int)B->sa_cap[k]; a.cell_cap = (int)B->cell_cap[k];
-        const size_t grp_bytes = (((size_t)a.sa_cap * 4 + (size_t)a.cell_cap * 5) + 15) & ~(size_t)15;
-        const size_t smem = grp_bytes * ngroups;
+        a.grp_bytes = (int)B->grp_bytes[k];
+        const size_t smem = (size_t)a.grp_bytes * ngroups;
         int rc = 0;
         switch (L.ocw) {
             case 7: rc = launch_one<7, 32>(ctx, a, 3 - k, smem, a.n_list); break;
