@@ -39,9 +39,9 @@ struct PivotSet {
         int32_t ocw = -1;
         int32_t *lists = nullptr;            // device: concatenated node indices
         size_t lists_cap = 0;
-        int32_t count[4] = {0, 0, 0, 0};     // [0..2] v2 bins (3/2/1 CTAs per SM), [3] general kernel
-        int32_t start[4] = {0, 0, 0, 0};
-        int64_t grp_bytes[3] = {0, 0, 0};    // shared memory per node group in each v2 bin
+        int32_t count[5] = {0, 0, 0, 0, 0};  // [0..3] v2 bins (4/3/2/1 CTAs per SM), [4] general kernel
+        int32_t start[5] = {0, 0, 0, 0, 0};
+        int64_t grp_bytes[4] = {0, 0, 0, 0}; // shared memory per node group in each v2 bin
     } bins[2];
 };
 

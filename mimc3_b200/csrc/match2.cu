@@ -38,6 +38,7 @@ namespace {
 constexpr int kThreads = 256;
 constexpr unsigned char kComputed = 1, kVisible = 2, kListed = 4;
 constexpr int kMaxJobs = 32;
+constexpr int kPivCache = 64;
 
 struct Match2Args {
     const float *ref, *srch;
@@ -148,6 +149,7 @@ struct Ctl {
     int job[kMaxJobs];               // cells of the current round
     int2 part[NWARPS][kMaxJobs];     // per-warp integer partial sums (hi units, lo units)
     Sums partd[NWARPS];              // masked-path partials
+    int2 pivc[kPivCache];       // the node's first pivots (the state machine walks them serially)
     int m;                      // >0 fast round, <0 done, 0 unused
     int mode;                   // 0 fast round, 1 masked round
     unsigned int node;
@@ -213,26 +215,42 @@ __global__ void __launch_bounds__(kThreads, min_ctas(OCW)) match2_kernel(const M
         float *cval = sa + sa_elems;
         unsigned char *cflag = (unsigned char *)(cval + cell_elems);
 
-        // ---- stage the chip through shared memory into registers (extract_refchip :845-855) ----
-        for (int i = t; i < S * S; i += G) {
-            const int rr = i / S, cc = i - rr * S;
-            const int iv = v0 + rr - OCW, iu = u0 + cc - OCW;
-            sa[i] = (iu >= 0 && iu < a.W && iv >= 0 && iv < a.H) ? __ldg(&a.ref[(size_t)iv * a.W + iu]) : 0.0f;
+        // ---- chip and search-area statistics from the SATs (investigate_valid_grid :605-644); the loads
+        //      are issued first so that their latency hides behind the chip staging below ----------------
+        unsigned long long q_ss = 0, q_s = 0;
+        unsigned int q_nul = 0;
+        int q_area = 0, q_full = 0;
+        if (t == 0) {
+            const int x0 = max(u0 - OCW, 0), y0 = max(v0 - OCW, 0), x1 = min(u0 + OCW + 1, a.W), y1 = min(v0 + OCW + 1, a.H);
+            rect_query(a.sat_ref, W1, x0, y0, x1, y1, q_ss, q_s, q_nul);
+            q_area = max(x1 - x0, 0) * max(y1 - y0, 0); q_full = S * S;
+        } else if (t == 1) {   // written part of the search area: rows [0,Dy2-1) x columns [0,Dx2-1)
+            const int ax = su0 - dx2, ay = sv0 - dy2;
+            const int x0 = max(ax, 0), y0 = max(ay, 0), x1 = min(ax + Dx2 - 1, a.W), y1 = min(ay + Dy2 - 1, a.H);
+            rect_query(a.sat_srch, W1, x0, y0, x1, y1, q_ss, q_s, q_nul);
+            q_area = max(x1 - x0, 0) * max(y1 - y0, 0); q_full = Dx2 * Dy2;
         }
-        if (t < 32) {   // chip and search-area statistics from the SATs (investigate_valid_grid :605-644)
-            unsigned long long ss = 0, s = 0;
-            unsigned int nul = 0;
-            int area = 0, full = 0;
-            if (lane == 0) {
-                const int x0 = max(u0 - OCW, 0), y0 = max(v0 - OCW, 0), x1 = min(u0 + OCW + 1, a.W), y1 = min(v0 + OCW + 1, a.H);
-                rect_query(a.sat_ref, W1, x0, y0, x1, y1, ss, s, nul);
-                area = max(x1 - x0, 0) * max(y1 - y0, 0); full = S * S;
-            } else if (lane == 1) {   // written part of the search area: rows [0,Dy2-1) x columns [0,Dx2-1)
-                const int ax = su0 - dx2, ay = sv0 - dy2;
-                const int x0 = max(ax, 0), y0 = max(ay, 0), x1 = min(ax + Dx2 - 1, a.W), y1 = min(ay + Dy2 - 1, a.H);
-                rect_query(a.sat_srch, W1, x0, y0, x1, y1, ss, s, nul);
-                area = max(x1 - x0, 0) * max(y1 - y0, 0); full = Dx2 * Dy2;
+        for (int i = t; i < min(P, kPivCache); i += G) ctl.pivc[i] = piv[i];
+
+        // ---- stage the chip through shared memory into registers (extract_refchip :845-855) ----
+        if (u0 - OCW >= 0 && v0 - OCW >= 0 && u0 + OCW < a.W && v0 + OCW < a.H) {
+            const float *src0 = a.ref + (size_t)(v0 - OCW) * a.W + (u0 - OCW);
+#pragma unroll 4
+            for (int i = t; i < S * S; i += G) {
+                const int rr = i / S, cc = i - rr * S;
+                sa[i] = __ldg(src0 + (size_t)rr * a.W + cc);
             }
+        } else {
+            for (int i = t; i < S * S; i += G) {
+                const int rr = i / S, cc = i - rr * S;
+                const int iv = v0 + rr - OCW, iu = u0 + cc - OCW;
+                sa[i] = (iu >= 0 && iu < a.W && iv >= 0 && iv < a.H) ? __ldg(&a.ref[(size_t)iv * a.W + iu]) : 0.0f;
+            }
+        }
+        if (t < 32) {
+            const unsigned long long ss = q_ss, s = q_s;
+            const unsigned int nul = q_nul;
+            const int area = q_area, full = q_full;
             const int cnt = (int)nul + (full - area);   // pixels < 1e-10, zero fill included
             const int cnt_ref = __shfl_sync(0xffffffffu, cnt, 0), cnt_sa = __shfl_sync(0xffffffffu, cnt, 1);
             if (lane == 0) {
@@ -263,6 +281,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(OCW)) match2_kernel(const M
             for (int y = gwarp; y < Dy2 - 1; y += C::NWARPS) {
                 const float *src = src0 + (size_t)y * a.W;
                 float *dst = sa + y * pitch;
+#pragma unroll 4
                 for (int x = lane; x < pitch; x += 32) dst[x] = (x < Dx2 - 1) ? __ldg(&src[x]) : 0.0f;
             }
             if (gwarp == (Dy2 - 1) % C::NWARPS)
@@ -300,7 +319,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(OCW)) match2_kernel(const M
                 } else {
                     if (phase == 0) {
                         while (ip_batch < P && m <= kMaxJobs - 9) {
-                            const int2 pv = piv[ip_batch];
+                            const int2 pv = ip_batch < kPivCache ? ctl.pivc[ip_batch] : piv[ip_batch];
                             const int bx = a.sign * pv.x + dx2, by = a.sign * pv.y + dy2;
                             ip_batch++;
                             if (bx - OCW <= 1 || bx + OCW >= Dx2 - 1 || by - OCW <= 1 || by + OCW >= Dy2 - 1) continue;
@@ -325,7 +344,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(OCW)) match2_kernel(const M
                         for (;;) {
                             if (!in_pivot) {
                                 if (ip >= P) { m = -1; break; }
-                                const int2 pv = piv[ip];
+                                const int2 pv = ip < kPivCache ? ctl.pivc[ip] : piv[ip];
                                 px = a.sign * pv.x + dx2; py = a.sign * pv.y + dy2;   // :693-694
                                 nccmax = -2.0f; duv0 = -1; duv1 = -1; flag_new = 1;
                                 in_pivot = true;
@@ -570,7 +589,7 @@ static void build_bins(mimc3cu_ctx *ctx, PivotSet *ps, PivotSet::Bins &B, int oc
     for (int k = 0; k < 3; k++) {
         const int ctas = bin_ctas(ocw, k);
         size_t per_cta = (228 * 1024 - ctas * 1024) / ctas;          // 1 KB reserved per resident CTA
-        per_cta = std::min(per_cta, usable) - 4608;                  // static control blocks
+        per_cta = std::min(per_cta, usable) - 8192;                  // static control blocks + slack
         const size_t per_group = (per_cta / ngroups) & ~(size_t)15;
         B.grp_bytes[k] = (int64_t)per_group;
     }
