@@ -152,7 +152,7 @@ struct Ctl {
     int2 pivc[kPivCache];       // the node's first pivots (the state machine walks them serially)
     int m;                      // >0 fast round, <0 done, 0 unused
     int mode;                   // 0 fast round, 1 masked round
-    unsigned int node;
+    unsigned int node[2];       // dynamic node fetch, double-buffered: the next index is fetched a node ahead
     int valid;
     // chip constants from the reference SAT
     unsigned long long chip_ss, chip_s;
@@ -181,12 +181,12 @@ __global__ void __launch_bounds__(kThreads, min_ctas(OCW)) match2_kernel(const M
     const int len = active ? min(L, S - col0) : 0;
     const int W1 = a.W + 1;
 
-    for (;;) {
+    if (t == 0) ctl.node[0] = atomicAdd(a.counter, 1u);
+    for (int iter = 0;; iter++) {
         gsync<G>();
-        if (t == 0) ctl.node = atomicAdd(a.counter, 1u);
-        gsync<G>();
-        const unsigned int idx = ctl.node;
+        const unsigned int idx = ctl.node[iter & 1];
         if (idx >= (unsigned int)a.n_list) break;
+        if (t == 0) ctl.node[(iter + 1) & 1] = atomicAdd(a.counter, 1u);   // latency hidden behind this node
         const int g = a.node_list ? a.node_list[idx] : (int)idx;
 
         // ---- node geometry (uniform over the group) -----------------------------------------
