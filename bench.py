@@ -13,12 +13,13 @@ one pass of that path over every node of the workload.
   e2e    the same metric through the C-ABI host entry points with HOST buffers: pinned
          u16/u8 images and xyuvav copied H2D, host pivot generation, multi-match,
          postprocess, finalize, five planes copied D2H -- all inside the timed region.
-  roofline      dominant kernel = match_kernel; achieved = sum over attempts and nodes of
-                8*S^2*E flop (E = NCC cells the reference algorithm evaluates, counted by
-                the kernel and cross-checked against the oracle in tests) / summed
-                match-kernel durations (CUDA events recorded by the library around every
-                launch inside the timed region); peak = FP32 FMA throughput measured live
-                by an FMA micro-benchmark (MEASURED_PEAKS.json has no FP32 CUDA-core figure).
+  roofline      dominant kernel = the matcher (match2_kernel<ocw,G>, plus match_kernel for nodes
+                outside its class); achieved = sum over attempts and nodes of 8*S^2*E flop
+                (E = NCC cells the reference algorithm evaluates, counted by the kernel and
+                cross-checked against the oracle in tests) / summed matcher durations (CUDA
+                events recorded by the library around every attempt inside the timed
+                region); peak = FP32 FMA throughput measured live by an FMA micro-benchmark
+                (MEASURED_PEAKS.json has no FP32 CUDA-core figure).
   cpu_baseline  the UNMODIFIED reference (oracle/_ref/libmimc3ref.so, OpenMP, all host
                 threads) on a bounded node sample of the same workload.
 
@@ -361,7 +362,7 @@ def main():
             traffic = json.load(open(tfile)).get(args.workload)
         except Exception:
             traffic = None
-    roofline = {"bound": "fp32", "kernel": "match_kernel", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+    roofline = {"bound": "fp32", "kernel": "match2_kernel<ocw,G> (exact-FP32 DLC-NCC matcher; match_kernel for nodes outside its class)", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak_tf, "traffic": traffic,
                 "peak_source": "FP32 FMA micro-benchmark measured live on this GPU (mimc3cu_fp32_peak); MEASURED_PEAKS.json has no CUDA-core FP32 figure",
                 "algorithmic_flop_per_step": alg_flop_step, "algorithmic_flop_per_launch": alg_flop_step / 32.0,
@@ -425,7 +426,7 @@ def main():
     if rank == 0:
         line = {"metric": "grid nodes matched per second", "value": value, "unit": "nodes/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32 products, f64 accumulation (bit-exact vs the reference)", "data": "synthetic", "config": config,
+                "dtype": "f32 (exact two-float accumulation of the float products, f64 normalisation; bit-exact vs the reference)", "data": "synthetic", "config": config,
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "collectives": (dict(comm_stats, backend="nccl", pattern="neighbour halo rows + int32 counter all-reduce per sweep, final gather of 5 planes") if world > 1 else None),
                 "postprocess_stats": {"dpf1_sweeps": int(stats[0]), "pseudosmoothing_sweeps": int(stats[1]), "holes_after_dpf0": int(stats[2])} if stats is not None else None}
