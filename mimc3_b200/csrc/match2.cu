@@ -66,6 +66,15 @@ struct Match2Args {
     float min_dn;
 };
 
+#ifdef MIMC3CU_PROFILE
+__device__ unsigned long long g_prof[8];   // cycles: 0 node total, 1 staging, 2 produce, 3 compute(+wait), 4 finalize, 5 rounds, 6 nodes
+#define PROF_T(var) const long long var = clock64()
+#define PROF_ADD(slot, v) do { if (t == 0) atomicAdd(&g_prof[slot], (unsigned long long)(v)); } while (0)
+#else
+#define PROF_T(var)
+#define PROF_ADD(slot, v)
+#endif
+
 struct Sums {
     double sx, sy, sxx, syy, sxy;
     int n;
@@ -86,6 +95,37 @@ struct Cfg {
     static_assert(NSEG >= 1, "group too small for this chip");
     static_assert((L + 1) / 2 <= 16, "at most 16 pixels per FP32 accumulator");
 };
+
+// Copies `rows` x `width` floats (global row stride `gstride`) into a shared tile with row pitch
+// `spitch` (columns [width, spitch) are zero-filled), NT threads, thread index `tix`.  Loads are
+// issued eight at a time before the first store: staging is latency-bound, not bandwidth-bound.
+template <int NT>
+__device__ __forceinline__ void stage_rows(const float *__restrict__ src, int gstride, float *dst, int spitch, int rows, int width,
+                                           int tix) {
+    const int total = rows * spitch;
+    int y = tix / spitch, x = tix - y * spitch;
+    const int dy = NT / spitch, dx = NT - dy * spitch;
+    for (int e = tix; e < total; e += NT * 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const bool ok = e + u * NT < total && x < width;
+            v[u] = ok ? __ldg(src + (size_t)y * gstride + x) : 0.0f;
+            x += dx; y += dy;
+            if (x >= spitch) { x -= spitch; y++; }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            if (e + u * NT < total) dst[e + u * NT] = v[u];
+    }
+}
+
+// Order-preserving map float -> uint32 (NaN -> 0), for warp arg-max with REDUX.
+__device__ __forceinline__ unsigned int ordered_key(float v) {
+    if (v != v) return 0u;
+    const unsigned int b = __float_as_uint(v + 0.0f);   // -0.0f -> +0.0f
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
 
 template <int G>
 __device__ __forceinline__ void gsync() {
@@ -188,6 +228,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(OCW)) match2_kernel(const M
         if (idx >= (unsigned int)a.n_list) break;
         if (t == 0) ctl.node[(iter + 1) & 1] = atomicAdd(a.counter, 1u);   // latency hidden behind this node
         const int g = a.node_list ? a.node_list[idx] : (int)idx;
+        PROF_T(t_node0);
 
         // ---- node geometry (uniform over the group) -----------------------------------------
         const int pb = a.csr_off[g], P = a.csr_off[g + 1] - pb;
@@ -234,12 +275,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(OCW)) match2_kernel(const M
 
         // ---- stage the chip through shared memory into registers (extract_refchip :845-855) ----
         if (u0 - OCW >= 0 && v0 - OCW >= 0 && u0 + OCW < a.W && v0 + OCW < a.H) {
-            const float *src0 = a.ref + (size_t)(v0 - OCW) * a.W + (u0 - OCW);
-#pragma unroll 4
-            for (int i = t; i < S * S; i += G) {
-                const int rr = i / S, cc = i - rr * S;
-                sa[i] = __ldg(src0 + (size_t)rr * a.W + cc);
-            }
+            stage_rows<G>(a.ref + (size_t)(v0 - OCW) * a.W + (u0 - OCW), a.W, sa, S, S, S, t);
         } else {
             for (int i = t; i < S * S; i += G) {
                 const int rr = i / S, cc = i - rr * S;
@@ -277,15 +313,8 @@ __global__ void __launch_bounds__(kThreads, min_ctas(OCW)) match2_kernel(const M
         //      never-written last row / column, zero in the pad columns [Dx2, pitch) ----------------
         if (su0 - dx2 >= 0 && sv0 - dy2 >= 0 && su0 - dx2 + Dx2 - 1 <= a.W && sv0 - dy2 + Dy2 - 1 <= a.H) {
             // written part entirely inside the image (the common case): no per-pixel bounds tests
-            const float *src0 = a.srch + (size_t)(sv0 - dy2) * a.W + (su0 - dx2);
-            for (int y = gwarp; y < Dy2 - 1; y += C::NWARPS) {
-                const float *src = src0 + (size_t)y * a.W;
-                float *dst = sa + y * pitch;
-#pragma unroll 4
-                for (int x = lane; x < pitch; x += 32) dst[x] = (x < Dx2 - 1) ? __ldg(&src[x]) : 0.0f;
-            }
-            if (gwarp == (Dy2 - 1) % C::NWARPS)
-                for (int x = lane; x < pitch; x += 32) sa[(Dy2 - 1) * pitch + x] = 0.0f;
+            stage_rows<G>(a.srch + (size_t)(sv0 - dy2) * a.W + (su0 - dx2), a.W, sa, pitch, Dy2 - 1, Dx2 - 1, t);
+            for (int x = t; x < pitch; x += G) sa[(Dy2 - 1) * pitch + x] = 0.0f;
         } else {
             for (int y = gwarp; y < Dy2; y += C::NWARPS) {
                 const int iv = sv0 - dy2 + y;
@@ -309,7 +338,10 @@ __global__ void __launch_bounds__(kThreads, min_ctas(OCW)) match2_kernel(const M
         bool in_pivot = false;
         int nslow = 0;                            // masked-path cells pending in ctl.job[0..nslow)
 
+        PROF_T(t_stage1);
+        PROF_ADD(1, t_stage1 - t_node0);
         for (;;) {
+            PROF_T(t_p0);
             if (gwarp == 0) {
                 int m = 0, mode = 0;
                 if (nslow > 0) {
@@ -378,11 +410,15 @@ __global__ void __launch_bounds__(kThreads, min_ctas(OCW)) match2_kernel(const M
                             const unsigned int newm = __ballot_sync(0xffffffffu, isnew);
                             if (isnew) cflag[cell] = f | kVisible;
                             flag_new = __popc(newm); ncells += flag_new;
+                            // :736-741: sequential strict `>` scan == first occurrence of the maximum, taken
+                            // only if it beats the running nccmax (NaN never wins)
                             duv0 = 0; duv1 = 0;
-#pragma unroll
-                            for (int k = 0; k < 9; k++) {
-                                const float vk = __shfl_sync(0xffffffffu, v, k);
-                                if (vk > nccmax) { nccmax = vk; duv0 = k / 3 - 1; duv1 = k % 3 - 1; }   // :736-741
+                            {
+                                const unsigned int key = lane < 9 ? ordered_key(v) : 0u;
+                                const unsigned int mx = __reduce_max_sync(0xffffffffu, key);
+                                const int kb = __ffs(__ballot_sync(0xffffffffu, lane < 9 && key == mx)) - 1;
+                                const float vb = __shfl_sync(0xffffffffu, v, kb);
+                                if (vb > nccmax) { nccmax = vb; duv0 = kb / 3 - 1; duv1 = kb % 3 - 1; }
                             }
                             px += duv0; py += duv1;                                            // :744-745
                             __syncwarp();
@@ -391,9 +427,12 @@ __global__ void __launch_bounds__(kThreads, min_ctas(OCW)) match2_kernel(const M
                 }
                 if (lane == 0) { ctl.m = m; ctl.mode = mode; }
             }
+            PROF_T(t_p1);
+            PROF_ADD(2, t_p1 - t_p0);
             gsync<G>();
             const int m = ctl.m, mode = ctl.mode;
             if (m < 0) break;
+            PROF_ADD(5, 1);
             if (m == 0) continue;   // batch produced nothing new; warp 0 switches to the climb
 
             if (mode == 0) {
@@ -442,6 +481,8 @@ __global__ void __launch_bounds__(kThreads, min_ctas(OCW)) match2_kernel(const M
                     if (lane == 0) ctl.part[gwarp][c] = make_int2((int)hi, lo);
                 }
                 gsync<G>();
+                PROF_T(t_c1);
+                PROF_ADD(3, t_c1 - t_p1);
                 // ---- finalize: lane c of warp 0 normalises cell c --------------------------------------
                 if (gwarp == 0) {
                     bool slowc = false;
@@ -473,6 +514,8 @@ __global__ void __launch_bounds__(kThreads, min_ctas(OCW)) match2_kernel(const M
                     nslow = __popc(sm);
                     __syncwarp();
                 }
+                PROF_T(t_f1);
+                PROF_ADD(4, t_f1 - t_c1);
             } else {
                 // ---- masked round: the reference's 5-sum loop with null exclusion (:719-733), FP64 ------
                 for (int c = 0; c < m; c++) {
@@ -539,6 +582,9 @@ __global__ void __launch_bounds__(kThreads, min_ctas(OCW)) match2_kernel(const M
             if (a.peak) a.peak[g] = make_int2(peak_x - dx2, peak_y - dy2);
             if (a.ncell) a.ncell[g] = ncells;
         }
+        PROF_T(t_node1);
+        PROF_ADD(0, t_node1 - t_node0);
+        PROF_ADD(6, 1);
     }
 }
 
@@ -680,6 +726,19 @@ int launch_match2(mimc3cu_ctx *ctx, const MatchLaunch &L, const Image *ref, cons
         }
         if (rc) return rc;
     }
+#ifdef MIMC3CU_PROFILE
+    {
+        unsigned long long h[8];
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpyFromSymbol(h, g_prof, sizeof(h));
+        if (h[6])
+            fprintf(stderr, "[prof ocw %d] nodes %llu rounds/node %.2f  cycles/node: total %.0f staging %.0f produce %.0f compute %.0f finalize %.0f\n",
+                    L.ocw, h[6], (double)h[5] / h[6], (double)h[0] / h[6], (double)h[1] / h[6], (double)h[2] / h[6], (double)h[3] / h[6],
+                    (double)h[4] / h[6]);
+        memset(h, 0, sizeof(h));
+        cudaMemcpyToSymbol(g_prof, h, sizeof(h));
+    }
+#endif
     // whatever did not fit goes to the general kernel (device-side count)
     MatchLaunch L1 = L;
     L1.node_list = ctx->overflow_list; L1.list_count = ctx->counter + 8; L1.list_n = 0;
