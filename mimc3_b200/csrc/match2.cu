@@ -37,7 +37,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr unsigned char kComputed = 1, kVisible = 2, kListed = 4;
-constexpr int kMaxJobs = 32;
+constexpr int kMaxJobsCap = 64;   // upper bound of cells per evaluation round (Cfg::MAXJ is per chip size)
 constexpr int kPivCache = 64;
 
 struct Match2Args {
@@ -92,6 +92,10 @@ struct Cfg {
     static constexpr int L = (S + NSEG - 1) / NSEG;
     static constexpr int NGROUPS = kThreads / G;
     static constexpr int NWARPS = G / 32;
+    // cells per evaluation round: 64 lets the ~39 first-probe cells of a static node go in one round
+    // (worth it for the biggest chip, where a round is long); 32 keeps the control block small
+    static constexpr int MAXJ = OCW == 40 ? 64 : 32;
+    static constexpr int NH = MAXJ / 32;
     static_assert(NSEG >= 1, "group too small for this chip");
     static_assert((L + 1) / 2 <= 16, "at most 16 pixels per FP32 accumulator");
 };
@@ -184,10 +188,10 @@ __device__ void subpixel_fit(const float n9[9], int peak_du, int peak_dv, float 
 }
 
 // Per-group control block in shared memory.
-template <int NWARPS>
+template <int NWARPS, int MAXJ>
 struct Ctl {
-    int job[kMaxJobs];               // cells of the current round
-    int2 part[NWARPS][kMaxJobs];     // per-warp integer partial sums (hi units, lo units)
+    int job[MAXJ];                   // cells of the current round
+    int2 part[NWARPS][MAXJ];         // per-warp integer partial sums (hi units, lo units)
     Sums partd[NWARPS];              // masked-path partials
     int2 pivc[kPivCache];       // the node's first pivots (the state machine walks them serially)
     int m;                      // >0 fast round, <0 done, 0 unused
@@ -204,12 +208,12 @@ __global__ void __launch_bounds__(kThreads, min_ctas(OCW)) match2_kernel(const M
     using C = Cfg<OCW, G>;
     constexpr int S = C::S, L = C::L;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ Ctl<C::NWARPS> ctl_all[C::NGROUPS];
+    __shared__ Ctl<C::NWARPS, C::MAXJ> ctl_all[C::NGROUPS];
 
     const int tid = threadIdx.x;
     const int grp = tid / G, t = tid - grp * G;
     const int lane = tid & 31, gwarp = t >> 5;
-    Ctl<C::NWARPS> &ctl = ctl_all[grp];
+    Ctl<C::NWARPS, C::MAXJ> &ctl = ctl_all[grp];
 
     // dynamic shared memory, per group and per node: sa[Dy2*pitch] floats | cval[cells] floats | cflag[cells] bytes
     float *sa = (float *)(smem_raw + (size_t)grp * a.grp_bytes);
@@ -350,7 +354,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(OCW)) match2_kernel(const M
                     nslow = 0;
                 } else {
                     if (phase == 0) {
-                        while (ip_batch < P && m <= kMaxJobs - 9) {
+                        while (ip_batch < P && m <= C::MAXJ - 9) {
                             const int2 pv = ip_batch < kPivCache ? ctl.pivc[ip_batch] : piv[ip_batch];
                             const int bx = a.sign * pv.x + dx2, by = a.sign * pv.y + dy2;
                             ip_batch++;
@@ -438,17 +442,25 @@ __global__ void __launch_bounds__(kThreads, min_ctas(OCW)) match2_kernel(const M
             if (mode == 0) {
                 // ---- fast round: sum(fl(r*s)) for m cells, exact in FP32 ------------------------------
                 // SAT corner loads for cell `lane` are issued first so their latency hides behind the loop
-                unsigned long long w_ss = 0, w_s = 0;
-                unsigned int w_nul = 1;
-                bool w_inside = false;
-                if (gwarp == 0 && lane < m) {
-                    const int job = ctl.job[lane];
-                    const int cy = job >> 16, cx = job & 0xffff;
-                    const int x0 = cx + 1, y0 = cy + 1;                       // window origin in the search area
-                    const int ix0 = su0 - dx2 + x0, iy0 = sv0 - dy2 + y0;     // ... and in the image
-                    w_inside = (x0 + S - 1 <= Dx2 - 2) && (y0 + S - 1 <= Dy2 - 2) && ix0 >= 0 && iy0 >= 0 &&
-                               ix0 + S <= a.W && iy0 + S <= a.H;
-                    if (w_inside) rect_query(a.sat_srch, W1, ix0, iy0, ix0 + S, iy0 + S, w_ss, w_s, w_nul);
+                unsigned long long w_ss[C::NH], w_s[C::NH];
+                unsigned int w_nul[C::NH];
+                bool w_inside[C::NH];
+#pragma unroll
+                for (int h = 0; h < C::NH; h++) { w_ss[h] = 0; w_s[h] = 0; w_nul[h] = 1; w_inside[h] = false; }
+                if (gwarp == 0) {
+#pragma unroll
+                    for (int h = 0; h < C::NH; h++) {
+                        const int slot = lane + 32 * h;
+                        if (slot < m) {
+                            const int job = ctl.job[slot];
+                            const int cy = job >> 16, cx = job & 0xffff;
+                            const int x0 = cx + 1, y0 = cy + 1;                       // window origin in the search area
+                            const int ix0 = su0 - dx2 + x0, iy0 = sv0 - dy2 + y0;     // ... and in the image
+                            w_inside[h] = (x0 + S - 1 <= Dx2 - 2) && (y0 + S - 1 <= Dy2 - 2) && ix0 >= 0 && iy0 >= 0 &&
+                                          ix0 + S <= a.W && iy0 + S <= a.H;
+                            if (w_inside[h]) rect_query(a.sat_srch, W1, ix0, iy0, ix0 + S, iy0 + S, w_ss[h], w_s[h], w_nul[h]);
+                        }
+                    }
                 }
                 for (int c = 0; c < m; c++) {
                     const int job = ctl.job[c];
@@ -485,34 +497,45 @@ __global__ void __launch_bounds__(kThreads, min_ctas(OCW)) match2_kernel(const M
                 PROF_ADD(3, t_c1 - t_p1);
                 // ---- finalize: lane c of warp 0 normalises cell c --------------------------------------
                 if (gwarp == 0) {
-                    bool slowc = false;
-                    int job = 0;
-                    if (lane < m) {
-                        job = ctl.job[lane];
-                        const int cell = (job >> 16) * cw + (job & 0xffff);
-                        if (ctl.chip_fast && w_inside && w_nul == 0) {
-                            long long hs = 0, ls = 0;
+                    int jobs[C::NH];
+                    bool slowc[C::NH];
 #pragma unroll
-                            for (int w = 0; w < C::NWARPS; w++) {
-                                const int2 q = ctl.part[w][lane];
-                                hs += (unsigned int)q.x; ls += q.y;
+                    for (int h = 0; h < C::NH; h++) { jobs[h] = 0; slowc[h] = false; }
+#pragma unroll
+                    for (int h = 0; h < C::NH; h++) {
+                        const int slot = lane + 32 * h;
+                        if (slot < m) {
+                            jobs[h] = ctl.job[slot];
+                            const int cell = (jobs[h] >> 16) * cw + (jobs[h] & 0xffff);
+                            if (ctl.chip_fast && w_inside[h] && w_nul[h] == 0) {
+                                long long hs = 0, ls = 0;
+#pragma unroll
+                                for (int w = 0; w < C::NWARPS; w++) {
+                                    const int2 q = ctl.part[w][slot];
+                                    hs += (unsigned int)q.x; ls += q.y;
+                                }
+                                Sums s;
+                                s.n = S * S;
+                                s.sxy = (double)hs * a.hi_unit + (double)ls * a.lo_unit;
+                                s.sx = (double)ctl.chip_s * a.inv_ref; s.sxx = (double)ctl.chip_ss * a.inv_ref2;
+                                s.sy = (double)w_s[h] * a.inv_srch; s.syy = (double)w_ss[h] * a.inv_srch2;
+                                cval[cell] = ncc_from_sums(s);
+                                cflag[cell] |= kComputed;
+                            } else {
+                                slowc[h] = true;
                             }
-                            Sums s;
-                            s.n = S * S;
-                            s.sxy = (double)hs * a.hi_unit + (double)ls * a.lo_unit;
-                            s.sx = (double)ctl.chip_s * a.inv_ref; s.sxx = (double)ctl.chip_ss * a.inv_ref2;
-                            s.sy = (double)w_s * a.inv_srch; s.syy = (double)w_ss * a.inv_srch2;
-                            cval[cell] = ncc_from_sums(s);
-                            cflag[cell] |= kComputed;
-                        } else {
-                            slowc = true;
                         }
                     }
-                    const unsigned int sm = __ballot_sync(0xffffffffu, slowc);
-                    __syncwarp();
-                    if (slowc) ctl.job[__popc(sm & ((1u << lane) - 1u))] = job;   // compacted in place (index <= lane)
-                    nslow = __popc(sm);
-                    __syncwarp();
+                    // slow cells are compacted in place: the target index never exceeds the slot it came from
+                    nslow = 0;
+#pragma unroll
+                    for (int h = 0; h < C::NH; h++) {
+                        const unsigned int smh = __ballot_sync(0xffffffffu, slowc[h]);
+                        __syncwarp();
+                        if (slowc[h]) ctl.job[nslow + __popc(smh & ((1u << lane) - 1u))] = jobs[h];
+                        nslow += __popc(smh);
+                        __syncwarp();
+                    }
                 }
                 PROF_T(t_f1);
                 PROF_ADD(4, t_f1 - t_c1);
@@ -635,7 +658,7 @@ static void build_bins(mimc3cu_ctx *ctx, PivotSet *ps, PivotSet::Bins &B, int oc
     for (int k = 0; k < 3; k++) {
         const int ctas = bin_ctas(ocw, k);
         size_t per_cta = (228 * 1024 - ctas * 1024) / ctas;          // 1 KB reserved per resident CTA
-        per_cta = std::min(per_cta, usable) - 8192;                  // static control blocks + slack
+        per_cta = std::min(per_cta, usable) - 12288;                 // static control blocks + slack
         const size_t per_group = (per_cta / ngroups) & ~(size_t)15;
         B.grp_bytes[k] = (int64_t)per_group;
     }
