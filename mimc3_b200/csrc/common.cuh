@@ -39,9 +39,10 @@ struct PivotSet {
         int32_t ocw = -1;
         int32_t *lists = nullptr;            // device: concatenated node indices
         size_t lists_cap = 0;
-        int32_t count[5] = {0, 0, 0, 0, 0};  // [0..3] v2 bins (4/3/2/1 CTAs per SM), [4] general kernel
-        int32_t start[5] = {0, 0, 0, 0, 0};
-        int64_t grp_bytes[4] = {0, 0, 0, 0}; // shared memory per node group in each v2 bin
+        int32_t count[6] = {0, 0, 0, 0, 0, 0};  // [0..4] v2 bins (match2.cu bin_table), [5] general kernel
+        int32_t start[6] = {0, 0, 0, 0, 0, 0};
+        int64_t grp_bytes[5] = {0, 0, 0, 0, 0}; // shared memory per node group in each v2 bin
+        int64_t max_global_cells = 0;        // largest cmap (cells, padded) among the bin-2 nodes that keep it in global memory
     } bins[2];
 };
 

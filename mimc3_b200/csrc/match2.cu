@@ -60,6 +60,7 @@ struct Match2Args {
     int *overflow_list;             // nodes that do not fit this launch's shared memory
     unsigned int *overflow_count;
     int grp_bytes;                  // shared memory per group: search area + cmap values + cmap flags
+    int ngroups;                    // node groups per CTA in this launch (blockDim.x / G)
     float A0, Mlo;                  // accumulator biases
     unsigned int A0_bits, Mlo_bits;
     double hi_unit, lo_unit;
@@ -618,25 +619,36 @@ float min_dn_float() {
 }
 
 template <int OCW, int G>
-int launch_one(mimc3cu_ctx *ctx, Match2Args &a, int per_sm_target, size_t smem, int n_list) {
+int launch_one(mimc3cu_ctx *ctx, Match2Args &a, int groups_per_cta, size_t smem, int n_list, long long *grid_out) {
     auto kern = match2_kernel<OCW, G>;
+    const int threads = G * groups_per_cta;   // <= kThreads; the kernel only needs whole groups
     CU_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+    CU_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem));
     if (per_sm < 1) return mimc3cu_fail(ctx, "match2: kernel does not fit on an SM (smem %zu)", smem);
-    (void)per_sm_target;
     long long grid = (long long)per_sm * ctx->num_sms;
-    const long long groups = ((long long)n_list + Cfg<OCW, G>::NGROUPS - 1) / Cfg<OCW, G>::NGROUPS;
+    const long long groups = ((long long)n_list + groups_per_cta - 1) / groups_per_cta;
     if (grid > groups) grid = groups;
-    kern<<<(unsigned)grid, kThreads, smem, ctx->stream>>>(a);
+    if (grid_out) *grid_out = grid;
+    kern<<<(unsigned)grid, threads, smem, ctx->stream>>>(a);
     ctx->launches++;
     CU_CHECK(ctx, cudaGetLastError());
     return 0;
 }
 
 inline int group_size(int ocw) { return ocw >= 30 ? 256 : 32; }
-// resident CTAs per SM that bin k is sized for
-inline int bin_ctas(int ocw, int k) { return k == 0 ? (ocw == 40 ? 3 : 4) : (k == 1 ? 2 : 1); }
+
+// Shared-memory bins of a launch: bin k runs `groups` node groups per CTA and is sized so that
+// `ctas` CTAs fit on an SM.  A node goes to the first bin it fits; the warp-per-node kernels get
+// two extra bins with few warps per CTA so that wide search areas (fast glaciers) stay on this
+// kernel instead of falling back to the general FP64 one.
+struct BinCfg { int groups, ctas; };
+constexpr int kMaxBins = 5;
+inline int bin_table(int ocw, BinCfg *t) {
+    if (ocw >= 30) { t[0] = {1, ocw == 40 ? 3 : 4}; t[1] = {1, 2}; t[2] = {1, 1}; return 3; }
+    t[0] = {8, ocw == 7 ? 4 : 2}; t[1] = {8, 2}; t[2] = {8, 1}; t[3] = {2, 2}; t[4] = {1, 1};
+    return 5;
+}
 
 }  // namespace
 
@@ -651,32 +663,32 @@ bool match2_supported(const MatchLaunch &L, const Image *ref, const Image *srch)
     return b + ref->frac_bits + srch->frac_bits <= 37;
 }
 
-// Per-launch shared-memory classes: bin k holds the nodes that fit when bin_ctas(G, k) CTAs share an SM.
 static void build_bins(mimc3cu_ctx *ctx, PivotSet *ps, PivotSet::Bins &B, int ocw) {
-    const int G = group_size(ocw), ngroups = kThreads / G;
+    BinCfg tab[kMaxBins];
+    const int nb = bin_table(ocw, tab);
     const size_t usable = ctx->smem_optin;
-    for (int k = 0; k < 3; k++) {
-        const int ctas = bin_ctas(ocw, k);
-        size_t per_cta = (228 * 1024 - ctas * 1024) / ctas;          // 1 KB reserved per resident CTA
-        per_cta = std::min(per_cta, usable) - 12288;                 // static control blocks + slack
-        const size_t per_group = (per_cta / ngroups) & ~(size_t)15;
-        B.grp_bytes[k] = (int64_t)per_group;
+    for (int k = 0; k < nb; k++) {
+        size_t per_cta = (228 * 1024 - tab[k].ctas * 1024) / tab[k].ctas;   // 1 KB reserved per resident CTA
+        per_cta = std::min(per_cta, usable) - 12288;                        // static control blocks + slack
+        B.grp_bytes[k] = (int64_t)((per_cta / tab[k].groups) & ~(size_t)15);
     }
     // two passes (count, then fill) over the host copy of the last pivots
     std::vector<uint8_t> which((size_t)ps->n);
-    int64_t cnt[4] = {0, 0, 0, 0};
+    B.max_global_cells = 0;
+    int64_t cnt[kMaxBins + 1] = {0, 0, 0, 0, 0, 0};
     for (int32_t g = 0; g < ps->n; g++) {
         const int64_t Dx2 = 2 * (ps->last_u[g] + ocw + 2) + 1, Dy2 = 2 * (ps->last_v[g] + ocw + 2) + 1;
         const int64_t pitch = (Dx2 + 3) | 1, need_sa = (Dy2 * pitch + 3) & ~3LL;
         const int64_t need_cells = ((Dx2 - 2 * ocw - 1) * (Dy2 - 2 * ocw - 1) + 15) & ~15LL;
         const int64_t need = need_sa * 4 + need_cells * 5;   // same formula as the kernel's fit test
         int k = 0;
-        while (k < 3 && need > B.grp_bytes[k]) k++;
+        while (k < nb && need > B.grp_bytes[k]) k++;
+        if (k == nb) k = kMaxBins;   // general kernel
         which[g] = (uint8_t)k; cnt[k]++;
     }
     std::vector<int32_t> all((size_t)ps->n);
-    int64_t pos[4];
-    for (int k = 0, acc = 0; k < 4; k++) { B.start[k] = acc; B.count[k] = (int32_t)cnt[k]; pos[k] = acc; acc += (int)cnt[k]; }
+    int64_t pos[kMaxBins + 1];
+    for (int k = 0, acc = 0; k <= kMaxBins; k++) { B.start[k] = acc; B.count[k] = (int32_t)cnt[k]; pos[k] = acc; acc += (int)cnt[k]; }
     for (int32_t g = 0; g < ps->n; g++) all[(size_t)pos[which[g]]++] = g;
     if ((size_t)ps->n > B.lists_cap) {
         if (B.lists) cudaFree(B.lists);
@@ -725,26 +737,28 @@ int launch_match2(mimc3cu_ctx *ctx, const MatchLaunch &L, const Image *ref, cons
     // counters: [0] general kernel, [1..3] the v2 bins, [8] overflow count (seeded with bin 3)
     CU_CHECK(ctx, cudaMemsetAsync(ctx->counter, 0, 16 * sizeof(unsigned int), ctx->stream));
     a.overflow_list = ctx->overflow_list; a.overflow_count = ctx->counter + 8;
-    if (B->count[3] > 0) {
-        CU_CHECK(ctx, cudaMemcpyAsync(ctx->overflow_list, B->lists + B->start[3], sizeof(int) * (size_t)B->count[3],
+    if (B->count[kMaxBins] > 0) {
+        CU_CHECK(ctx, cudaMemcpyAsync(ctx->overflow_list, B->lists + B->start[kMaxBins], sizeof(int) * (size_t)B->count[kMaxBins],
                                       cudaMemcpyDeviceToDevice, ctx->stream));
-        unsigned int c3 = (unsigned int)B->count[3];
+        unsigned int c3 = (unsigned int)B->count[kMaxBins];
         // small H2D from the stack is safe: the value is copied at enqueue time for pageable memory
         CU_CHECK(ctx, cudaMemcpyAsync(ctx->counter + 8, &c3, sizeof(c3), cudaMemcpyHostToDevice, ctx->stream));
     }
-    const int G = group_size(L.ocw), ngroups = kThreads / G;
-    for (int k = 0; k < 3; k++) {
+    BinCfg tab[kMaxBins];
+    const int nb = bin_table(L.ocw, tab);
+    for (int k = 0; k < nb; k++) {
         if (B->count[k] == 0) continue;
         a.node_list = B->lists + B->start[k]; a.n_list = B->count[k];
         a.counter = ctx->counter + 1 + k;
         a.grp_bytes = (int)B->grp_bytes[k];
-        const size_t smem = (size_t)a.grp_bytes * ngroups;
+        a.ngroups = tab[k].groups;
+        const size_t smem = (size_t)a.grp_bytes * tab[k].groups;
         int rc = 0;
         switch (L.ocw) {
-            case 7: rc = launch_one<7, 32>(ctx, a, 3 - k, smem, a.n_list); break;
-            case 15: rc = launch_one<15, 32>(ctx, a, 3 - k, smem, a.n_list); break;
-            case 30: rc = launch_one<30, 256>(ctx, a, 3 - k, smem, a.n_list); break;
-            case 40: rc = launch_one<40, 256>(ctx, a, 3 - k, smem, a.n_list); break;
+            case 7: rc = launch_one<7, 32>(ctx, a, tab[k].groups, smem, a.n_list, nullptr); break;
+            case 15: rc = launch_one<15, 32>(ctx, a, tab[k].groups, smem, a.n_list, nullptr); break;
+            case 30: rc = launch_one<30, 256>(ctx, a, tab[k].groups, smem, a.n_list, nullptr); break;
+            case 40: rc = launch_one<40, 256>(ctx, a, tab[k].groups, smem, a.n_list, nullptr); break;
             default: return mimc3cu_fail(ctx, "match2: unsupported ocw %d", L.ocw);
         }
         if (rc) return rc;
@@ -765,7 +779,7 @@ int launch_match2(mimc3cu_ctx *ctx, const MatchLaunch &L, const Image *ref, cons
     // whatever did not fit goes to the general kernel (device-side count)
     MatchLaunch L1 = L;
     L1.node_list = ctx->overflow_list; L1.list_count = ctx->counter + 8; L1.list_n = 0;
-    if (B->count[3] == 0) {
+    if (B->count[kMaxBins] == 0) {
         // nothing pre-seeded and the v2 kernels only overflow if host and device sizing disagree;
         // still run a minimal grid so that such nodes are never dropped
         L1.n = std::min<int32_t>(L.n, ctx->num_sms);
