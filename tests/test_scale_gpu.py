@@ -1,0 +1,80 @@
+"""Size-independent properties at a benchmark-like size (4096x4096 u16, ~40 k nodes, all four chip
+sizes), where the CPU oracle would take minutes: (1) the two CUDA implementations of the cell
+evaluator -- general FP64 and exact-FP32 + SAT, which share no arithmetic -- agree bit for bit on
+dp, integer peaks and evaluated-cell counts; (2) the recovered displacements match the known
+synthetic shift field; (3) the swapped pass is the mirror image of the forward pass on a pair
+without displacement gradient."""
+import numpy as np
+import pytest
+import torch
+
+from mimc3_b200 import lib, synth
+from tests.util import VEC_OCW, same_bits_nan_aware
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def big():
+    sc = synth.make_scene(H=4096, W=4096, dtype="u16", spacing=20, seed=404, peak_px=6.3, device="cuda")
+    return sc
+
+
+def run(ctx, sc, mode, a, b, offset, sign, slot, ocw):
+    n = sc.n
+    dp = torch.empty((n, 3), device="cuda"); pk = torch.empty((n, 2), dtype=torch.int32, device="cuda")
+    nc = torch.empty(n, dtype=torch.int32, device="cuda")
+    ctx.set_matcher(mode)
+    ctx.match_async(a, b, offset, slot, sign, ocw, False, dp, pk, nc)
+    ctx.sync()
+    assert ctx.last_matcher() == (2 if mode == "v2" else 1)
+    ctx.set_matcher("auto")
+    return dp.cpu().numpy(), pk.cpu().numpy(), nc.cpu().numpy()
+
+
+def test_two_kernels_agree_and_recover_the_shift_field(gpu_ctx, big):
+    sc = big
+    H, W = sc.shape
+    p = lib.params_for(sc.xyuvav, sc.dimx, sc.dimy, sc.dt)
+    gpu_ctx.set_nodes(sc.xyuvav)
+    a, b = gpu_ctx.image_from(sc.i0), gpu_ctx.image_from(sc.i1)
+    offset = np.array(sc.offset, np.int32)
+    try:
+        for slot, ocw in enumerate(VEC_OCW):
+            off, piv = lib.get_uv_pivot(sc.xyuvav, sc.dt, p.mpp, ocw, H, W)
+            gpu_ctx.set_pivots(slot, off, piv)
+            d2, k2, c2 = run(gpu_ctx, sc, "v2", a, b, offset, +1, slot, ocw)
+            d1, k1, c1 = run(gpu_ctx, sc, "v1", a, b, offset, +1, slot, ocw)
+            assert np.array_equal(k1, k2) and np.array_equal(c1, c2), ocw
+            assert same_bits_nan_aware(d1, d2), ocw
+            # accuracy against the known shift field (total displacement minus the CP offset)
+            err = np.hypot(d2[:, 0] - (sc.truth_du.ravel() - sc.offset[0]), d2[:, 1] - (sc.truth_dv.ravel() - sc.offset[1]))
+            ok = d2[:, 2] > 0.5
+            assert ok.mean() > 0.97
+            assert np.median(err[ok]) < (0.12 if ocw == 7 else 0.06), (ocw, np.median(err[ok]))
+            assert c2.min() >= 39        # at least the first probes of 11 pivots: 3 * (P + 2) cells
+    finally:
+        gpu_ctx.image_destroy(a); gpu_ctx.image_destroy(b)
+
+
+def test_swapped_pass_mirrors_forward_pass_for_identical_images(gpu_ctx, big):
+    """i1 == i0 shifted by a pure integer offset => forward (i0->i1, +offset) and swapped
+    (i1->i0, -offset, negated pivots) find peaks that are exact mirror images."""
+    sc = big
+    H, W = sc.shape
+    i0 = sc.i0
+    i1 = torch.roll(i0, shifts=(3, -5), dims=(0, 1)).contiguous()      # content moves by (du, dv) = (-5, +3)
+    p = lib.params_for(sc.xyuvav, sc.dimx, sc.dimy, sc.dt)
+    gpu_ctx.set_nodes(sc.xyuvav)
+    a, b = gpu_ctx.image_from(i0), gpu_ctx.image_from(i1)
+    offset = np.array((-5, 3), np.int32)
+    try:
+        off, piv = lib.get_uv_pivot(sc.xyuvav, sc.dt, p.mpp, 30, H, W)
+        gpu_ctx.set_pivots(0, off, piv)
+        df, kf, _ = run(gpu_ctx, sc, "v2", a, b, offset, +1, 0, 30)
+        ds, ks, _ = run(gpu_ctx, sc, "v2", b, a, -offset, -1, 0, 30)
+        inner = (sc.xyuvav[:, 2] > 200) & (sc.xyuvav[:, 2] < W - 200) & (sc.xyuvav[:, 3] > 200) & (sc.xyuvav[:, 3] < H - 200)
+        assert (kf[inner] == 0).all() and (ks[inner] == 0).all()           # the integer offset explains everything
+        assert np.allclose(df[inner, 2], 1.0, atol=1e-6) and np.allclose(ds[inner, 2], 1.0, atol=1e-6)
+    finally:
+        gpu_ctx.image_destroy(a); gpu_ctx.image_destroy(b)
