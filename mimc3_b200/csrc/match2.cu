@@ -200,7 +200,8 @@ struct Ctl {
     unsigned int node[2];       // dynamic node fetch, double-buffered: the next index is fetched a node ahead
     int valid;
     // chip constants from the reference SAT
-    unsigned long long chip_ss, chip_s;
+    // sum(fl(r*r)), sum(r) of the chip without its last (tx) column / (ty) row: index tx + 2*ty
+    unsigned long long chip_ss[4], chip_s[4];
     int chip_fast;
 };
 
@@ -270,6 +271,10 @@ __global__ void __launch_bounds__(kThreads, min_ctas(OCW)) match2_kernel(const M
             const int x0 = max(u0 - OCW, 0), y0 = max(v0 - OCW, 0), x1 = min(u0 + OCW + 1, a.W), y1 = min(v0 + OCW + 1, a.H);
             rect_query(a.sat_ref, W1, x0, y0, x1, y1, q_ss, q_s, q_nul);
             q_area = max(x1 - x0, 0) * max(y1 - y0, 0); q_full = S * S;
+        } else if (t >= 2 && t <= 4) {   // the chip without its last column (t=2: tx), last row (t=3: ty), or both (t=4)
+            const int tx = (t - 1) & 1, ty = (t - 1) >> 1;
+            const int x0 = max(u0 - OCW, 0), y0 = max(v0 - OCW, 0), x1 = min(u0 + OCW + 1 - tx, a.W), y1 = min(v0 + OCW + 1 - ty, a.H);
+            rect_query(a.sat_ref, W1, x0, y0, x1, y1, q_ss, q_s, q_nul);
         } else if (t == 1) {   // written part of the search area: rows [0,Dy2-1) x columns [0,Dx2-1)
             const int ax = su0 - dx2, ay = sv0 - dy2;
             const int x0 = max(ax, 0), y0 = max(ay, 0), x1 = min(ax + Dx2 - 1, a.W), y1 = min(ay + Dy2 - 1, a.H);
@@ -296,9 +301,10 @@ __global__ void __launch_bounds__(kThreads, min_ctas(OCW)) match2_kernel(const M
             const int cnt_ref = __shfl_sync(0xffffffffu, cnt, 0), cnt_sa = __shfl_sync(0xffffffffu, cnt, 1);
             if (lane == 0) {
                 ctl.valid = !(((float)cnt_ref / (float)(S * S) > 0.8f) || ((float)cnt_sa / (float)(Dx2 * Dy2) > 0.8f));
-                ctl.chip_ss = ss; ctl.chip_s = s;
+                ctl.chip_ss[0] = ss; ctl.chip_s[0] = s;
                 ctl.chip_fast = (cnt == 0);
             }
+            if (lane >= 2 && lane <= 4) { ctl.chip_ss[lane - 1] = ss; ctl.chip_s[lane - 1] = s; }
         }
         gsync<G>();
         if (!ctl.valid) {
@@ -446,8 +452,9 @@ __global__ void __launch_bounds__(kThreads, min_ctas(OCW)) match2_kernel(const M
                 unsigned long long w_ss[C::NH], w_s[C::NH];
                 unsigned int w_nul[C::NH];
                 bool w_inside[C::NH];
+                int w_trim[C::NH];   // tx + 2*ty: the window reaches the never-written last column / row of the search area
 #pragma unroll
-                for (int h = 0; h < C::NH; h++) { w_ss[h] = 0; w_s[h] = 0; w_nul[h] = 1; w_inside[h] = false; }
+                for (int h = 0; h < C::NH; h++) { w_ss[h] = 0; w_s[h] = 0; w_nul[h] = 1; w_inside[h] = false; w_trim[h] = 0; }
                 if (gwarp == 0) {
 #pragma unroll
                     for (int h = 0; h < C::NH; h++) {
@@ -457,9 +464,14 @@ __global__ void __launch_bounds__(kThreads, min_ctas(OCW)) match2_kernel(const M
                             const int cy = job >> 16, cx = job & 0xffff;
                             const int x0 = cx + 1, y0 = cy + 1;                       // window origin in the search area
                             const int ix0 = su0 - dx2 + x0, iy0 = sv0 - dy2 + y0;     // ... and in the image
-                            w_inside[h] = (x0 + S - 1 <= Dx2 - 2) && (y0 + S - 1 <= Dy2 - 2) && ix0 >= 0 && iy0 >= 0 &&
-                                          ix0 + S <= a.W && iy0 + S <= a.H;
-                            if (w_inside[h]) rect_query(a.sat_srch, W1, ix0, iy0, ix0 + S, iy0 + S, w_ss[h], w_s[h], w_nul[h]);
+                            // The last column / row of the search area is never written by the reference
+                            // (H1): those pixels are nulls, i.e. the joint mask simply drops the chip's last
+                            // column / row.  The FP32 loop already sees zeros there; only the SAT rectangles
+                            // and n shrink.
+                            const int tx = (x0 + S - 1 == Dx2 - 1), ty = (y0 + S - 1 == Dy2 - 1);
+                            w_trim[h] = tx + 2 * ty;
+                            w_inside[h] = ix0 >= 0 && iy0 >= 0 && ix0 + S - tx <= a.W && iy0 + S - ty <= a.H;
+                            if (w_inside[h]) rect_query(a.sat_srch, W1, ix0, iy0, ix0 + S - tx, iy0 + S - ty, w_ss[h], w_s[h], w_nul[h]);
                         }
                     }
                 }
@@ -516,9 +528,9 @@ __global__ void __launch_bounds__(kThreads, min_ctas(OCW)) match2_kernel(const M
                                     hs += (unsigned int)q.x; ls += q.y;
                                 }
                                 Sums s;
-                                s.n = S * S;
+                                s.n = (S - (w_trim[h] & 1)) * (S - (w_trim[h] >> 1));
                                 s.sxy = (double)hs * a.hi_unit + (double)ls * a.lo_unit;
-                                s.sx = (double)ctl.chip_s * a.inv_ref; s.sxx = (double)ctl.chip_ss * a.inv_ref2;
+                                s.sx = (double)ctl.chip_s[w_trim[h]] * a.inv_ref; s.sxx = (double)ctl.chip_ss[w_trim[h]] * a.inv_ref2;
                                 s.sy = (double)w_s[h] * a.inv_srch; s.syy = (double)w_ss[h] * a.inv_srch2;
                                 cval[cell] = ncc_from_sums(s);
                                 cflag[cell] |= kComputed;
