@@ -195,6 +195,14 @@ struct Ctl {
     int2 part[NWARPS][MAXJ];         // per-warp integer partial sums (hi units, lo units)
     Sums partd[NWARPS];              // masked-path partials
     int2 pivc[kPivCache];       // the node's first pivots (the state machine walks them serially)
+    // Node geometry and the climb state live HERE, not in registers: only the leader warp needs
+    // them, and only between evaluation rounds; keeping them out of the register file of the
+    // compute loop is what lets the 81x81 instantiation keep its chip pixels without remat/spills.
+    struct Geo { int g, P, su0, sv0, dx2, dy2, Dx2, Dy2, cw, ch, sa_elems, cell_elems; const int2 *piv; } geo;
+    struct Climb {
+        int ip_batch, phase, ip, px, py, duv0, duv1, flag_new, peak_x, peak_y, ncells, in_pivot, nslow;
+        float nccmax, best;
+    } st;
     int m;                      // >0 fast round, <0 done, 0 unused
     int mode;                   // 0 fast round, 1 masked round
     unsigned int node[2];       // dynamic node fetch, double-buffered: the next index is fetched a node ahead
@@ -204,6 +212,315 @@ struct Ctl {
     unsigned long long chip_ss[4], chip_s[4];
     int chip_fast;
 };
+
+// Evaluation rounds of one node: driven by warp 0 of the group (the reference's state machine),
+// executed by all of the group's threads.  Geometry and climb state are read from / written to the
+// control block inside the leader-only sections, so the compute loop keeps only the chip pixels,
+// the tile pointer and the pitch in registers.
+template <int OCW, int G, typename CtlT>
+__device__ __forceinline__ void node_rounds(const Match2Args &a, CtlT &ctl, float *sa, const float (&chip)[Cfg<OCW, G>::L],
+                                            const int pitch, const int r, const int col0, const bool active, const int t,
+                                            const int lane, const int gwarp) {
+    using C = Cfg<OCW, G>;
+    constexpr int S = C::S, L = C::L;
+    const int W1 = a.W + 1;
+    {
+        for (;;) {
+            PROF_T(t_p0);
+            if (gwarp == 0) {
+                // geometry + climb state: shared memory -> registers for the duration of this block only
+                const int P = ctl.geo.P, dx2 = ctl.geo.dx2, dy2 = ctl.geo.dy2, Dx2 = ctl.geo.Dx2, Dy2 = ctl.geo.Dy2, cw = ctl.geo.cw;
+                const int2 *piv = ctl.geo.piv;
+                float *cval = sa + ctl.geo.sa_elems;
+                unsigned char *cflag = (unsigned char *)(cval + ctl.geo.cell_elems);
+                int ip_batch = ctl.st.ip_batch, phase = ctl.st.phase, ip = ctl.st.ip, px = ctl.st.px, py = ctl.st.py;
+                int duv0 = ctl.st.duv0, duv1 = ctl.st.duv1, flag_new = ctl.st.flag_new, peak_x = ctl.st.peak_x, peak_y = ctl.st.peak_y;
+                int ncells = ctl.st.ncells, nslow = ctl.st.nslow;
+                bool in_pivot = ctl.st.in_pivot != 0;
+                float nccmax = ctl.st.nccmax, best = ctl.st.best;
+                __syncwarp();
+                int m = 0, mode = 0;
+                if (nslow > 0) {
+                    // masked re-evaluation of the cells the fast path could not take
+                    mode = 1; m = nslow;   // ctl.job[0..nslow) was filled by the finalize step below
+                    nslow = 0;
+                } else {
+                    if (phase == 0) {
+                        while (ip_batch < P && m <= C::MAXJ - 9) {
+                            const int2 pv = ip_batch < kPivCache ? ctl.pivc[ip_batch] : piv[ip_batch];
+                            const int bx = a.sign * pv.x + dx2, by = a.sign * pv.y + dy2;
+                            ip_batch++;
+                            if (bx - OCW <= 1 || bx + OCW >= Dx2 - 1 || by - OCW <= 1 || by + OCW >= Dy2 - 1) continue;
+                            bool want = false;
+                            int cell = 0;
+                            if (lane < 9) {
+                                cell = (by + (lane % 3 - 1) - OCW - 1) * cw + (bx + (lane / 3 - 1) - OCW - 1);
+                                want = !(cflag[cell] & (kComputed | kListed));
+                            }
+                            const unsigned int wm = __ballot_sync(0xffffffffu, want);
+                            if (want) {
+                                ctl.job[m + __popc(wm & ((1u << lane) - 1u))] = ((by + (lane % 3 - 1) - OCW - 1) << 16) | (bx + (lane / 3 - 1) - OCW - 1);
+                                cflag[cell] |= kListed;
+                            }
+                            m += __popc(wm);
+                            __syncwarp();
+                        }
+                        if (m == 0 && ip_batch >= P) phase = 1;
+                    }
+                    if (phase == 1) {
+                        // the reference's state machine, MIMC_module.c:691-753
+                        for (;;) {
+                            if (!in_pivot) {
+                                if (ip >= P) { m = -1; break; }
+                                const int2 pv = ip < kPivCache ? ctl.pivc[ip] : piv[ip];
+                                px = a.sign * pv.x + dx2; py = a.sign * pv.y + dy2;   // :693-694
+                                nccmax = -2.0f; duv0 = -1; duv1 = -1; flag_new = 1;
+                                in_pivot = true;
+                            }
+                            bool stop = !((duv0 != 0 || duv1 != 0) && flag_new != 0);       // :699
+                            if (!stop && (px - OCW <= 1 || px + OCW >= Dx2 - 1 || py - OCW <= 1 || py + OCW >= Dy2 - 1)) {
+                                duv0 = 0; duv1 = 0; stop = true;                             // :701-707 (break)
+                            }
+                            if (stop) {
+                                if (nccmax > best) { peak_x = px; peak_y = py; best = nccmax; }   // :747-752
+                                in_pivot = false; ip++;
+                                continue;
+                            }
+                            // lane k < 9 looks at probe cell k = (c1+1)*3 + (c2+1)  (c1: u outer, c2: v inner)
+                            int cell = 0;
+                            unsigned char f = kComputed;
+                            float v = 0.0f;
+                            if (lane < 9) {
+                                cell = (py + (lane % 3 - 1) - OCW - 1) * cw + (px + (lane / 3 - 1) - OCW - 1);
+                                f = cflag[cell];
+                                v = cval[cell];
+                            }
+                            const bool need = !(f & (kVisible | kComputed));
+                            const unsigned int nm = __ballot_sync(0xffffffffu, need);
+                            if (nm) {
+                                if (need) ctl.job[__popc(nm & ((1u << lane) - 1u))] = ((py + (lane % 3 - 1) - OCW - 1) << 16) | (px + (lane / 3 - 1) - OCW - 1);
+                                m = __popc(nm);
+                                break;
+                            }
+                            const bool isnew = lane < 9 && (!(f & kVisible) || v < -1.0f);   // `cmap < -1.0` => evaluated now, :713
+                            const unsigned int newm = __ballot_sync(0xffffffffu, isnew);
+                            if (isnew) cflag[cell] = f | kVisible;
+                            flag_new = __popc(newm); ncells += flag_new;
+                            // :736-741: sequential strict `>` scan == first occurrence of the maximum, taken
+                            // only if it beats the running nccmax (NaN never wins)
+                            duv0 = 0; duv1 = 0;
+                            {
+                                const unsigned int key = lane < 9 ? ordered_key(v) : 0u;
+                                const unsigned int mx = __reduce_max_sync(0xffffffffu, key);
+                                const int kb = __ffs(__ballot_sync(0xffffffffu, lane < 9 && key == mx)) - 1;
+                                const float vb = __shfl_sync(0xffffffffu, v, kb);
+                                if (vb > nccmax) { nccmax = vb; duv0 = kb / 3 - 1; duv1 = kb % 3 - 1; }
+                            }
+                            px += duv0; py += duv1;                                            // :744-745
+                            __syncwarp();
+                        }
+                    }
+                }
+                if (lane == 0) {
+                    ctl.m = m; ctl.mode = mode;
+                    ctl.st = {ip_batch, phase, ip, px, py, duv0, duv1, flag_new, peak_x, peak_y, ncells, in_pivot ? 1 : 0, nslow, nccmax, best};
+                }
+            }
+            PROF_T(t_p1);
+            PROF_ADD(2, t_p1 - t_p0);
+            gsync<G>();
+            const int m = ctl.m, mode = ctl.mode;
+            if (m < 0) break;
+            PROF_ADD(5, 1);
+            if (m == 0) continue;   // batch produced nothing new; warp 0 switches to the climb
+
+            if (mode == 0) {
+                // ---- fast round: sum(fl(r*s)) for m cells, exact in FP32 ------------------------------
+                // SAT corner loads for cell `lane` are issued first so their latency hides behind the loop
+                unsigned long long w_ss[C::NH], w_s[C::NH];
+                unsigned int w_nul[C::NH];
+                bool w_inside[C::NH];
+                int w_trim[C::NH];   // tx + 2*ty: the window reaches the never-written last column / row of the search area
+#pragma unroll
+                for (int h = 0; h < C::NH; h++) { w_ss[h] = 0; w_s[h] = 0; w_nul[h] = 1; w_inside[h] = false; w_trim[h] = 0; }
+                if (gwarp == 0) {
+                    const int su0 = ctl.geo.su0, sv0 = ctl.geo.sv0, dx2 = ctl.geo.dx2, dy2 = ctl.geo.dy2, Dx2 = ctl.geo.Dx2, Dy2 = ctl.geo.Dy2;
+#pragma unroll
+                    for (int h = 0; h < C::NH; h++) {
+                        const int slot = lane + 32 * h;
+                        if (slot < m) {
+                            const int job = ctl.job[slot];
+                            const int cy = job >> 16, cx = job & 0xffff;
+                            const int x0 = cx + 1, y0 = cy + 1;                       // window origin in the search area
+                            const int ix0 = su0 - dx2 + x0, iy0 = sv0 - dy2 + y0;     // ... and in the image
+                            // The last column / row of the search area is never written by the reference
+                            // (H1): those pixels are nulls, i.e. the joint mask simply drops the chip's last
+                            // column / row.  The FP32 loop already sees zeros there; only the SAT rectangles
+                            // and n shrink.
+                            const int tx = (x0 + S - 1 == Dx2 - 1), ty = (y0 + S - 1 == Dy2 - 1);
+                            w_trim[h] = tx + 2 * ty;
+                            w_inside[h] = ix0 >= 0 && iy0 >= 0 && ix0 + S - tx <= a.W && iy0 + S - ty <= a.H;
+                            if (w_inside[h]) rect_query(a.sat_srch, W1, ix0, iy0, ix0 + S - tx, iy0 + S - ty, w_ss[h], w_s[h], w_nul[h]);
+                        }
+                    }
+                }
+                for (int c = 0; c < m; c++) {
+                    const int job = ctl.job[c];
+                    const int cy = job >> 16, cx = job & 0xffff;
+                    unsigned int hi = 0;
+                    int lo = 0;
+                    if (active) {
+                        const float *sp = sa + (cy + 1 + r) * pitch + (cx + 1 + col0);
+                        float acc0 = a.A0, acc1 = a.A0, lo0 = a.Mlo, lo1 = a.Mlo;
+#pragma unroll
+                        for (int k = 0; k < L; k++) {
+                            const float p = __fmul_rn(chip[k], sp[k]);
+                            if (k & 1) {
+                                const float s1 = __fadd_rn(acc1, p);
+                                const float z = __fsub_rn(s1, acc1);
+                                lo1 = __fadd_rn(lo1, __fsub_rn(p, z));
+                                acc1 = s1;
+                            } else {
+                                const float s1 = __fadd_rn(acc0, p);
+                                const float z = __fsub_rn(s1, acc0);
+                                lo0 = __fadd_rn(lo0, __fsub_rn(p, z));
+                                acc0 = s1;
+                            }
+                        }
+                        hi = (__float_as_uint(acc0) - a.A0_bits) + (__float_as_uint(acc1) - a.A0_bits);
+                        lo = (int)(__float_as_uint(lo0) - a.Mlo_bits) + (int)(__float_as_uint(lo1) - a.Mlo_bits);
+                    }
+                    hi = __reduce_add_sync(0xffffffffu, hi);
+                    lo = __reduce_add_sync(0xffffffffu, lo);
+                    if (lane == 0) ctl.part[gwarp][c] = make_int2((int)hi, lo);
+                }
+                gsync<G>();
+                PROF_T(t_c1);
+                PROF_ADD(3, t_c1 - t_p1);
+                // ---- finalize: lane c of warp 0 normalises cell c --------------------------------------
+                if (gwarp == 0) {
+                    const int cw = ctl.geo.cw;
+                    float *cval = sa + ctl.geo.sa_elems;
+                    unsigned char *cflag = (unsigned char *)(cval + ctl.geo.cell_elems);
+                    int nslow = 0;
+                    int jobs[C::NH];
+                    bool slowc[C::NH];
+#pragma unroll
+                    for (int h = 0; h < C::NH; h++) { jobs[h] = 0; slowc[h] = false; }
+#pragma unroll
+                    for (int h = 0; h < C::NH; h++) {
+                        const int slot = lane + 32 * h;
+                        if (slot < m) {
+                            jobs[h] = ctl.job[slot];
+                            const int cell = (jobs[h] >> 16) * cw + (jobs[h] & 0xffff);
+                            if (ctl.chip_fast && w_inside[h] && w_nul[h] == 0) {
+                                long long hs = 0, ls = 0;
+#pragma unroll
+                                for (int w = 0; w < C::NWARPS; w++) {
+                                    const int2 q = ctl.part[w][slot];
+                                    hs += (unsigned int)q.x; ls += q.y;
+                                }
+                                Sums s;
+                                s.n = (S - (w_trim[h] & 1)) * (S - (w_trim[h] >> 1));
+                                s.sxy = (double)hs * a.hi_unit + (double)ls * a.lo_unit;
+                                s.sx = (double)ctl.chip_s[w_trim[h]] * a.inv_ref; s.sxx = (double)ctl.chip_ss[w_trim[h]] * a.inv_ref2;
+                                s.sy = (double)w_s[h] * a.inv_srch; s.syy = (double)w_ss[h] * a.inv_srch2;
+                                cval[cell] = ncc_from_sums(s);
+                                cflag[cell] |= kComputed;
+                            } else {
+                                slowc[h] = true;
+                            }
+                        }
+                    }
+                    // slow cells are compacted in place: the target index never exceeds the slot it came from
+#pragma unroll
+                    for (int h = 0; h < C::NH; h++) {
+                        const unsigned int smh = __ballot_sync(0xffffffffu, slowc[h]);
+                        __syncwarp();
+                        if (slowc[h]) ctl.job[nslow + __popc(smh & ((1u << lane) - 1u))] = jobs[h];
+                        nslow += __popc(smh);
+                        __syncwarp();
+                    }
+                    if (lane == 0) ctl.st.nslow = nslow;
+                    __syncwarp();
+                }
+                PROF_T(t_f1);
+                PROF_ADD(4, t_f1 - t_c1);
+            } else {
+                // ---- masked round: the reference's 5-sum loop with null exclusion (:719-733), FP64 ------
+                float *cval = sa + ctl.geo.sa_elems;
+                unsigned char *cflag = (unsigned char *)(cval + ctl.geo.cell_elems);
+                for (int c = 0; c < m; c++) {
+                    const int job = ctl.job[c];
+                    const int cy = job >> 16, cx = job & 0xffff;
+                    const int cell = cy * ctl.geo.cw + cx;
+                    Sums s = {0.0, 0.0, 0.0, 0.0, 0.0, 0};
+                    if (active) {
+                        const float *sp = sa + (cy + 1 + r) * pitch + (cx + 1 + col0);
+#pragma unroll
+                        for (int k = 0; k < L; k++) {
+                            const float rv = chip[k], sv = sp[k];
+                            if (rv >= a.min_dn && sv >= a.min_dn) {   // null exclusion, :723
+                                s.n++;
+                                s.sx += (double)rv; s.sy += (double)sv;
+                                s.sxx += (double)__fmul_rn(rv, rv);
+                                s.syy += (double)__fmul_rn(sv, sv);
+                                s.sxy += (double)__fmul_rn(rv, sv);
+                            }
+                        }
+                    }
+                    s.n = __reduce_add_sync(0xffffffffu, s.n);
+                    s.sx = warp_sum_d(s.sx); s.sy = warp_sum_d(s.sy);
+                    s.sxx = warp_sum_d(s.sxx); s.syy = warp_sum_d(s.syy); s.sxy = warp_sum_d(s.sxy);
+                    if (G == 32) {
+                        if (lane == 0) { cval[cell] = ncc_from_sums(s); cflag[cell] |= kComputed; }
+                    } else {
+                        if (lane == 0) ctl.partd[gwarp] = s;
+                        gsync<G>();
+                        if (t == 0) {
+                            Sums q = ctl.partd[0];
+                            for (int w = 1; w < C::NWARPS; w++) {
+                                const Sums &z = ctl.partd[w];
+                                q.n += z.n; q.sx += z.sx; q.sy += z.sy; q.sxx += z.sxx; q.syy += z.syy; q.sxy += z.sxy;
+                            }
+                            cval[cell] = ncc_from_sums(q);
+                            cflag[cell] |= kComputed;
+                        }
+                        gsync<G>();
+                    }
+                }
+                if (G == 32) __syncwarp();
+            }
+        }
+
+        // ---- sub-pixel fit and output (:757-788) ------------------------------------------------------
+        if (t == 0) {
+            const int g = ctl.geo.g, dx2 = ctl.geo.dx2, dy2 = ctl.geo.dy2, cw = ctl.geo.cw, ch = ctl.geo.ch;
+            const int peak_x = ctl.st.peak_x, peak_y = ctl.st.peak_y, ncells = ctl.st.ncells;
+            const float best = ctl.st.best;
+            const float *cval = sa + ctl.geo.sa_elems;
+            const unsigned char *cflag = (const unsigned char *)(cval + ctl.geo.cell_elems);
+            float n9[9];
+            for (int rr = 0; rr < 3; rr++)
+                for (int cc = 0; cc < 3; cc++) {
+                    const int cx = peak_x - 1 + cc - (OCW + 1), cy = peak_y - 1 + rr - (OCW + 1);
+                    float v = -2.0f;   // never evaluated (or outside the evaluable region)
+                    if (cx >= 0 && cx < cw && cy >= 0 && cy < ch) {
+                        const int cell = cy * cw + cx;
+                        if (cflag[cell] & kVisible) v = cval[cell];
+                    }
+                    n9[rr * 3 + cc] = v;
+                }
+            float du, dv;
+            subpixel_fit(n9, peak_x - dx2, peak_y - dy2, du, dv);
+            a.dp[3 * (size_t)g] = a.negate * du;
+            a.dp[3 * (size_t)g + 1] = a.negate * dv;
+            a.dp[3 * (size_t)g + 2] = best;
+            if (a.peak) a.peak[g] = make_int2(peak_x - dx2, peak_y - dy2);
+            if (a.ncell) a.ncell[g] = ncells;
+        }
+    }
+}
 
 template <int OCW, int G>
 __global__ void __launch_bounds__(kThreads, min_ctas(OCW)) match2_kernel(const Match2Args a) {
@@ -340,284 +657,14 @@ __global__ void __launch_bounds__(kThreads, min_ctas(OCW)) match2_kernel(const M
         for (int i = t; i < cw * ch; i += G) cflag[i] = 0;
         gsync<G>();
 
-        // ---- evaluation rounds driven by warp 0 of the group ---------------------------------------
-        // state of the reference's hill climb (registers, uniform over warp 0)
-        int ip_batch = 0, phase = 0;              // phase 0: up-front first probes, 1: climb
-        int ip = 0, px = 0, py = 0, duv0 = -1, duv1 = -1, flag_new = 1;
-        int peak_x = dx2, peak_y = dy2, ncells = 0;
-        float nccmax = -2.0f, best = -2.0f;
-        bool in_pivot = false;
-        int nslow = 0;                            // masked-path cells pending in ctl.job[0..nslow)
-
+        if (t == 0) {
+            ctl.geo = {g, P, su0, sv0, dx2, dy2, Dx2, Dy2, cw, ch, sa_elems, cell_elems, piv};
+            // phase 0: up-front first probes, 1: the climb; nslow: masked-path cells pending in ctl.job[0..nslow)
+            ctl.st = {0, 0, 0, 0, 0, -1, -1, 1, dx2, dy2, 0, 0, 0, -2.0f, -2.0f};
+        }
         PROF_T(t_stage1);
         PROF_ADD(1, t_stage1 - t_node0);
-        for (;;) {
-            PROF_T(t_p0);
-            if (gwarp == 0) {
-                int m = 0, mode = 0;
-                if (nslow > 0) {
-                    // masked re-evaluation of the cells the fast path could not take
-                    mode = 1; m = nslow;   // ctl.job[0..nslow) was filled by the finalize step below
-                    nslow = 0;
-                } else {
-                    if (phase == 0) {
-                        while (ip_batch < P && m <= C::MAXJ - 9) {
-                            const int2 pv = ip_batch < kPivCache ? ctl.pivc[ip_batch] : piv[ip_batch];
-                            const int bx = a.sign * pv.x + dx2, by = a.sign * pv.y + dy2;
-                            ip_batch++;
-                            if (bx - OCW <= 1 || bx + OCW >= Dx2 - 1 || by - OCW <= 1 || by + OCW >= Dy2 - 1) continue;
-                            bool want = false;
-                            int cell = 0;
-                            if (lane < 9) {
-                                cell = (by + (lane % 3 - 1) - OCW - 1) * cw + (bx + (lane / 3 - 1) - OCW - 1);
-                                want = !(cflag[cell] & (kComputed | kListed));
-                            }
-                            const unsigned int wm = __ballot_sync(0xffffffffu, want);
-                            if (want) {
-                                ctl.job[m + __popc(wm & ((1u << lane) - 1u))] = ((by + (lane % 3 - 1) - OCW - 1) << 16) | (bx + (lane / 3 - 1) - OCW - 1);
-                                cflag[cell] |= kListed;
-                            }
-                            m += __popc(wm);
-                            __syncwarp();
-                        }
-                        if (m == 0 && ip_batch >= P) phase = 1;
-                    }
-                    if (phase == 1) {
-                        // the reference's state machine, MIMC_module.c:691-753
-                        for (;;) {
-                            if (!in_pivot) {
-                                if (ip >= P) { m = -1; break; }
-                                const int2 pv = ip < kPivCache ? ctl.pivc[ip] : piv[ip];
-                                px = a.sign * pv.x + dx2; py = a.sign * pv.y + dy2;   // :693-694
-                                nccmax = -2.0f; duv0 = -1; duv1 = -1; flag_new = 1;
-                                in_pivot = true;
-                            }
-                            bool stop = !((duv0 != 0 || duv1 != 0) && flag_new != 0);       // :699
-                            if (!stop && (px - OCW <= 1 || px + OCW >= Dx2 - 1 || py - OCW <= 1 || py + OCW >= Dy2 - 1)) {
-                                duv0 = 0; duv1 = 0; stop = true;                             // :701-707 (break)
-                            }
-                            if (stop) {
-                                if (nccmax > best) { peak_x = px; peak_y = py; best = nccmax; }   // :747-752
-                                in_pivot = false; ip++;
-                                continue;
-                            }
-                            // lane k < 9 looks at probe cell k = (c1+1)*3 + (c2+1)  (c1: u outer, c2: v inner)
-                            int cell = 0;
-                            unsigned char f = kComputed;
-                            float v = 0.0f;
-                            if (lane < 9) {
-                                cell = (py + (lane % 3 - 1) - OCW - 1) * cw + (px + (lane / 3 - 1) - OCW - 1);
-                                f = cflag[cell];
-                                v = cval[cell];
-                            }
-                            const bool need = !(f & (kVisible | kComputed));
-                            const unsigned int nm = __ballot_sync(0xffffffffu, need);
-                            if (nm) {
-                                if (need) ctl.job[__popc(nm & ((1u << lane) - 1u))] = ((py + (lane % 3 - 1) - OCW - 1) << 16) | (px + (lane / 3 - 1) - OCW - 1);
-                                m = __popc(nm);
-                                break;
-                            }
-                            const bool isnew = lane < 9 && (!(f & kVisible) || v < -1.0f);   // `cmap < -1.0` => evaluated now, :713
-                            const unsigned int newm = __ballot_sync(0xffffffffu, isnew);
-                            if (isnew) cflag[cell] = f | kVisible;
-                            flag_new = __popc(newm); ncells += flag_new;
-                            // :736-741: sequential strict `>` scan == first occurrence of the maximum, taken
-                            // only if it beats the running nccmax (NaN never wins)
-                            duv0 = 0; duv1 = 0;
-                            {
-                                const unsigned int key = lane < 9 ? ordered_key(v) : 0u;
-                                const unsigned int mx = __reduce_max_sync(0xffffffffu, key);
-                                const int kb = __ffs(__ballot_sync(0xffffffffu, lane < 9 && key == mx)) - 1;
-                                const float vb = __shfl_sync(0xffffffffu, v, kb);
-                                if (vb > nccmax) { nccmax = vb; duv0 = kb / 3 - 1; duv1 = kb % 3 - 1; }
-                            }
-                            px += duv0; py += duv1;                                            // :744-745
-                            __syncwarp();
-                        }
-                    }
-                }
-                if (lane == 0) { ctl.m = m; ctl.mode = mode; }
-            }
-            PROF_T(t_p1);
-            PROF_ADD(2, t_p1 - t_p0);
-            gsync<G>();
-            const int m = ctl.m, mode = ctl.mode;
-            if (m < 0) break;
-            PROF_ADD(5, 1);
-            if (m == 0) continue;   // batch produced nothing new; warp 0 switches to the climb
-
-            if (mode == 0) {
-                // ---- fast round: sum(fl(r*s)) for m cells, exact in FP32 ------------------------------
-                // SAT corner loads for cell `lane` are issued first so their latency hides behind the loop
-                unsigned long long w_ss[C::NH], w_s[C::NH];
-                unsigned int w_nul[C::NH];
-                bool w_inside[C::NH];
-                int w_trim[C::NH];   // tx + 2*ty: the window reaches the never-written last column / row of the search area
-#pragma unroll
-                for (int h = 0; h < C::NH; h++) { w_ss[h] = 0; w_s[h] = 0; w_nul[h] = 1; w_inside[h] = false; w_trim[h] = 0; }
-                if (gwarp == 0) {
-#pragma unroll
-                    for (int h = 0; h < C::NH; h++) {
-                        const int slot = lane + 32 * h;
-                        if (slot < m) {
-                            const int job = ctl.job[slot];
-                            const int cy = job >> 16, cx = job & 0xffff;
-                            const int x0 = cx + 1, y0 = cy + 1;                       // window origin in the search area
-                            const int ix0 = su0 - dx2 + x0, iy0 = sv0 - dy2 + y0;     // ... and in the image
-                            // The last column / row of the search area is never written by the reference
-                            // (H1): those pixels are nulls, i.e. the joint mask simply drops the chip's last
-                            // column / row.  The FP32 loop already sees zeros there; only the SAT rectangles
-                            // and n shrink.
-                            const int tx = (x0 + S - 1 == Dx2 - 1), ty = (y0 + S - 1 == Dy2 - 1);
-                            w_trim[h] = tx + 2 * ty;
-                            w_inside[h] = ix0 >= 0 && iy0 >= 0 && ix0 + S - tx <= a.W && iy0 + S - ty <= a.H;
-                            if (w_inside[h]) rect_query(a.sat_srch, W1, ix0, iy0, ix0 + S - tx, iy0 + S - ty, w_ss[h], w_s[h], w_nul[h]);
-                        }
-                    }
-                }
-                for (int c = 0; c < m; c++) {
-                    const int job = ctl.job[c];
-                    const int cy = job >> 16, cx = job & 0xffff;
-                    unsigned int hi = 0;
-                    int lo = 0;
-                    if (active) {
-                        const float *sp = sa + (cy + 1 + r) * pitch + (cx + 1 + col0);
-                        float acc0 = a.A0, acc1 = a.A0, lo0 = a.Mlo, lo1 = a.Mlo;
-#pragma unroll
-                        for (int k = 0; k < L; k++) {
-                            const float p = __fmul_rn(chip[k], sp[k]);
-                            if (k & 1) {
-                                const float s1 = __fadd_rn(acc1, p);
-                                const float z = __fsub_rn(s1, acc1);
-                                lo1 = __fadd_rn(lo1, __fsub_rn(p, z));
-                                acc1 = s1;
-                            } else {
-                                const float s1 = __fadd_rn(acc0, p);
-                                const float z = __fsub_rn(s1, acc0);
-                                lo0 = __fadd_rn(lo0, __fsub_rn(p, z));
-                                acc0 = s1;
-                            }
-                        }
-                        hi = (__float_as_uint(acc0) - a.A0_bits) + (__float_as_uint(acc1) - a.A0_bits);
-                        lo = (int)(__float_as_uint(lo0) - a.Mlo_bits) + (int)(__float_as_uint(lo1) - a.Mlo_bits);
-                    }
-                    hi = __reduce_add_sync(0xffffffffu, hi);
-                    lo = __reduce_add_sync(0xffffffffu, lo);
-                    if (lane == 0) ctl.part[gwarp][c] = make_int2((int)hi, lo);
-                }
-                gsync<G>();
-                PROF_T(t_c1);
-                PROF_ADD(3, t_c1 - t_p1);
-                // ---- finalize: lane c of warp 0 normalises cell c --------------------------------------
-                if (gwarp == 0) {
-                    int jobs[C::NH];
-                    bool slowc[C::NH];
-#pragma unroll
-                    for (int h = 0; h < C::NH; h++) { jobs[h] = 0; slowc[h] = false; }
-#pragma unroll
-                    for (int h = 0; h < C::NH; h++) {
-                        const int slot = lane + 32 * h;
-                        if (slot < m) {
-                            jobs[h] = ctl.job[slot];
-                            const int cell = (jobs[h] >> 16) * cw + (jobs[h] & 0xffff);
-                            if (ctl.chip_fast && w_inside[h] && w_nul[h] == 0) {
-                                long long hs = 0, ls = 0;
-#pragma unroll
-                                for (int w = 0; w < C::NWARPS; w++) {
-                                    const int2 q = ctl.part[w][slot];
-                                    hs += (unsigned int)q.x; ls += q.y;
-                                }
-                                Sums s;
-                                s.n = (S - (w_trim[h] & 1)) * (S - (w_trim[h] >> 1));
-                                s.sxy = (double)hs * a.hi_unit + (double)ls * a.lo_unit;
-                                s.sx = (double)ctl.chip_s[w_trim[h]] * a.inv_ref; s.sxx = (double)ctl.chip_ss[w_trim[h]] * a.inv_ref2;
-                                s.sy = (double)w_s[h] * a.inv_srch; s.syy = (double)w_ss[h] * a.inv_srch2;
-                                cval[cell] = ncc_from_sums(s);
-                                cflag[cell] |= kComputed;
-                            } else {
-                                slowc[h] = true;
-                            }
-                        }
-                    }
-                    // slow cells are compacted in place: the target index never exceeds the slot it came from
-                    nslow = 0;
-#pragma unroll
-                    for (int h = 0; h < C::NH; h++) {
-                        const unsigned int smh = __ballot_sync(0xffffffffu, slowc[h]);
-                        __syncwarp();
-                        if (slowc[h]) ctl.job[nslow + __popc(smh & ((1u << lane) - 1u))] = jobs[h];
-                        nslow += __popc(smh);
-                        __syncwarp();
-                    }
-                }
-                PROF_T(t_f1);
-                PROF_ADD(4, t_f1 - t_c1);
-            } else {
-                // ---- masked round: the reference's 5-sum loop with null exclusion (:719-733), FP64 ------
-                for (int c = 0; c < m; c++) {
-                    const int job = ctl.job[c];
-                    const int cy = job >> 16, cx = job & 0xffff;
-                    const int cell = cy * cw + cx;
-                    Sums s = {0.0, 0.0, 0.0, 0.0, 0.0, 0};
-                    if (active) {
-                        const float *sp = sa + (cy + 1 + r) * pitch + (cx + 1 + col0);
-#pragma unroll
-                        for (int k = 0; k < L; k++) {
-                            const float rv = chip[k], sv = sp[k];
-                            if (rv >= a.min_dn && sv >= a.min_dn) {   // null exclusion, :723
-                                s.n++;
-                                s.sx += (double)rv; s.sy += (double)sv;
-                                s.sxx += (double)__fmul_rn(rv, rv);
-                                s.syy += (double)__fmul_rn(sv, sv);
-                                s.sxy += (double)__fmul_rn(rv, sv);
-                            }
-                        }
-                    }
-                    s.n = __reduce_add_sync(0xffffffffu, s.n);
-                    s.sx = warp_sum_d(s.sx); s.sy = warp_sum_d(s.sy);
-                    s.sxx = warp_sum_d(s.sxx); s.syy = warp_sum_d(s.syy); s.sxy = warp_sum_d(s.sxy);
-                    if (G == 32) {
-                        if (lane == 0) { cval[cell] = ncc_from_sums(s); cflag[cell] |= kComputed; }
-                    } else {
-                        if (lane == 0) ctl.partd[gwarp] = s;
-                        gsync<G>();
-                        if (t == 0) {
-                            Sums q = ctl.partd[0];
-                            for (int w = 1; w < C::NWARPS; w++) {
-                                const Sums &z = ctl.partd[w];
-                                q.n += z.n; q.sx += z.sx; q.sy += z.sy; q.sxx += z.sxx; q.syy += z.syy; q.sxy += z.sxy;
-                            }
-                            cval[cell] = ncc_from_sums(q);
-                            cflag[cell] |= kComputed;
-                        }
-                        gsync<G>();
-                    }
-                }
-                if (G == 32) __syncwarp();
-            }
-        }
-
-        // ---- sub-pixel fit and output (:757-788) ------------------------------------------------------
-        if (t == 0) {
-            float n9[9];
-            for (int rr = 0; rr < 3; rr++)
-                for (int cc = 0; cc < 3; cc++) {
-                    const int cx = peak_x - 1 + cc - (OCW + 1), cy = peak_y - 1 + rr - (OCW + 1);
-                    float v = -2.0f;   // never evaluated (or outside the evaluable region)
-                    if (cx >= 0 && cx < cw && cy >= 0 && cy < ch) {
-                        const int cell = cy * cw + cx;
-                        if (cflag[cell] & kVisible) v = cval[cell];
-                    }
-                    n9[rr * 3 + cc] = v;
-                }
-            float du, dv;
-            subpixel_fit(n9, peak_x - dx2, peak_y - dy2, du, dv);
-            a.dp[3 * (size_t)g] = a.negate * du;
-            a.dp[3 * (size_t)g + 1] = a.negate * dv;
-            a.dp[3 * (size_t)g + 2] = best;
-            if (a.peak) a.peak[g] = make_int2(peak_x - dx2, peak_y - dy2);
-            if (a.ncell) a.ncell[g] = ncells;
-        }
+        node_rounds<OCW, G>(a, ctl, sa, chip, pitch, r, col0, active, t, lane, gwarp);
         PROF_T(t_node1);
         PROF_ADD(0, t_node1 - t_node0);
         PROF_ADD(6, 1);
