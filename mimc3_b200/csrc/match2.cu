@@ -84,7 +84,7 @@ struct Sums {
 // Resident CTAs per SM each instantiation is compiled for (register cap = 65536 / (256 * n)) and
 // that the first shared-memory bin is sized for: ocw 40 keeps 27 chip pixels per thread (80
 // registers, 3 CTAs), ocw 30 keeps 16 (64 registers, 4 CTAs); measured on B200 (profiles/).
-constexpr int min_ctas(int ocw) { return ocw == 15 ? 2 : 4; }
+constexpr int min_ctas(int ocw) { return ocw == 15 ? 2 : (ocw == 30 ? 5 : 4); }
 
 template <int OCW, int G>
 struct Cfg {
@@ -704,6 +704,7 @@ inline int group_size(int ocw) { return ocw >= 30 ? 256 : 32; }
 struct BinCfg { int groups, ctas; };
 constexpr int kMaxBins = 5;
 inline int bin_table(int ocw, BinCfg *t) {
+    if (ocw == 30) { t[0] = {1, 5}; t[1] = {1, 4}; t[2] = {1, 3}; t[3] = {1, 2}; t[4] = {1, 1}; return 5; }
     if (ocw >= 30) { t[0] = {1, 4}; t[1] = {1, 3}; t[2] = {1, 2}; t[3] = {1, 1}; return 4; }
     t[0] = {8, ocw == 7 ? 4 : 2}; t[1] = {8, 2}; t[2] = {8, 1}; t[3] = {2, 2}; t[4] = {1, 1};
     return 5;
