@@ -166,6 +166,16 @@ __device__ __forceinline__ void rect_query(const ulonglong2 *sat, int W1, int x0
     nul = (unsigned int)(pk & 0xffffffull);
 }
 
+// Same, leaving value sum and null count packed (fewer live registers for prefetched queries).
+__device__ __forceinline__ void rect_query_packed(const ulonglong2 *sat, int W1, int x0, int y0, int x1, int y1,
+                                                  unsigned long long &ss, unsigned long long &pk) {
+    if (x1 <= x0 || y1 <= y0) { ss = 0; pk = 0; return; }
+    const ulonglong2 a = __ldg(&sat[(size_t)y1 * W1 + x1]), b = __ldg(&sat[(size_t)y0 * W1 + x1]);
+    const ulonglong2 c = __ldg(&sat[(size_t)y1 * W1 + x0]), d = __ldg(&sat[(size_t)y0 * W1 + x0]);
+    ss = a.x - b.x - c.x + d.x;
+    pk = a.y - b.y - c.y + d.y;
+}
+
 // 3x3 quadratic fit, MIMC_module.c:757-788, with the reference's float/double mix (H7).
 __device__ void subpixel_fit(const float n9[9], int peak_du, int peak_dv, float &du, float &dv) {
 #define FM(k, x) __fmul_rn((float)(k), (x))
@@ -337,12 +347,12 @@ __device__ __forceinline__ void node_rounds(const Match2Args &a, CtlT &ctl, floa
             if (mode == 0) {
                 // ---- fast round: sum(fl(r*s)) for m cells, exact in FP32 ------------------------------
                 // SAT corner loads for cell `lane` are issued first so their latency hides behind the loop
-                unsigned long long w_ss[C::NH], w_s[C::NH];
-                unsigned int w_nul[C::NH];
-                bool w_inside[C::NH];
-                int w_trim[C::NH];   // tx + 2*ty: the window reaches the never-written last column / row of the search area
+                // per slot: sum(fl(s*s)), packed (sum(s) << 24 | nulls), flags = inside | (tx + 2*ty) << 1 where
+                // tx/ty say that the window reaches the never-written last column / row of the search area
+                unsigned long long w_ss[C::NH], w_pk[C::NH];
+                int w_flag[C::NH];
 #pragma unroll
-                for (int h = 0; h < C::NH; h++) { w_ss[h] = 0; w_s[h] = 0; w_nul[h] = 1; w_inside[h] = false; w_trim[h] = 0; }
+                for (int h = 0; h < C::NH; h++) { w_ss[h] = 0; w_pk[h] = 1; w_flag[h] = 0; }
                 if (gwarp == 0) {
                     const int su0 = ctl.geo.su0, sv0 = ctl.geo.sv0, dx2 = ctl.geo.dx2, dy2 = ctl.geo.dy2, Dx2 = ctl.geo.Dx2, Dy2 = ctl.geo.Dy2;
 #pragma unroll
@@ -358,9 +368,9 @@ __device__ __forceinline__ void node_rounds(const Match2Args &a, CtlT &ctl, floa
                             // column / row.  The FP32 loop already sees zeros there; only the SAT rectangles
                             // and n shrink.
                             const int tx = (x0 + S - 1 == Dx2 - 1), ty = (y0 + S - 1 == Dy2 - 1);
-                            w_trim[h] = tx + 2 * ty;
-                            w_inside[h] = ix0 >= 0 && iy0 >= 0 && ix0 + S - tx <= a.W && iy0 + S - ty <= a.H;
-                            if (w_inside[h]) rect_query(a.sat_srch, W1, ix0, iy0, ix0 + S - tx, iy0 + S - ty, w_ss[h], w_s[h], w_nul[h]);
+                            const bool inside = ix0 >= 0 && iy0 >= 0 && ix0 + S - tx <= a.W && iy0 + S - ty <= a.H;
+                            w_flag[h] = (inside ? 1 : 0) | ((tx + 2 * ty) << 1);
+                            if (inside) rect_query_packed(a.sat_srch, W1, ix0, iy0, ix0 + S - tx, iy0 + S - ty, w_ss[h], w_pk[h]);
                         }
                     }
                 }
@@ -413,7 +423,8 @@ __device__ __forceinline__ void node_rounds(const Match2Args &a, CtlT &ctl, floa
                         if (slot < m) {
                             jobs[h] = ctl.job[slot];
                             const int cell = (jobs[h] >> 16) * cw + (jobs[h] & 0xffff);
-                            if (ctl.chip_fast && w_inside[h] && w_nul[h] == 0) {
+                            const int trim = w_flag[h] >> 1;
+                            if (ctl.chip_fast && (w_flag[h] & 1) && (w_pk[h] & 0xffffffull) == 0) {
                                 long long hs = 0, ls = 0;
 #pragma unroll
                                 for (int w = 0; w < C::NWARPS; w++) {
@@ -421,10 +432,10 @@ __device__ __forceinline__ void node_rounds(const Match2Args &a, CtlT &ctl, floa
                                     hs += (unsigned int)q.x; ls += q.y;
                                 }
                                 Sums s;
-                                s.n = (S - (w_trim[h] & 1)) * (S - (w_trim[h] >> 1));
+                                s.n = (S - (trim & 1)) * (S - (trim >> 1));
                                 s.sxy = (double)hs * a.hi_unit + (double)ls * a.lo_unit;
-                                s.sx = (double)ctl.chip_s[w_trim[h]] * a.inv_ref; s.sxx = (double)ctl.chip_ss[w_trim[h]] * a.inv_ref2;
-                                s.sy = (double)w_s[h] * a.inv_srch; s.syy = (double)w_ss[h] * a.inv_srch2;
+                                s.sx = (double)ctl.chip_s[trim] * a.inv_ref; s.sxx = (double)ctl.chip_ss[trim] * a.inv_ref2;
+                                s.sy = (double)(w_pk[h] >> 24) * a.inv_srch; s.syy = (double)w_ss[h] * a.inv_srch2;
                                 cval[cell] = ncc_from_sums(s);
                                 cflag[cell] |= kComputed;
                             } else {
