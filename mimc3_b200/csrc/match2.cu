@@ -734,13 +734,26 @@ bool match2_supported(const MatchLaunch &L, const Image *ref, const Image *srch)
     return b + ref->frac_bits + srch->frac_bits <= 37;
 }
 
+static size_t static_smem_bytes(int ocw) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaErrorInvalidValue;
+    switch (ocw) {
+        case 7: e = cudaFuncGetAttributes(&fa, match2_kernel<7, 32>); break;
+        case 15: e = cudaFuncGetAttributes(&fa, match2_kernel<15, 32>); break;
+        case 30: e = cudaFuncGetAttributes(&fa, match2_kernel<30, 256>); break;
+        case 40: e = cudaFuncGetAttributes(&fa, match2_kernel<40, 256>); break;
+    }
+    return e == cudaSuccess ? fa.sharedSizeBytes : 12288;
+}
+
 static void build_bins(mimc3cu_ctx *ctx, PivotSet *ps, PivotSet::Bins &B, int ocw) {
     BinCfg tab[kMaxBins];
     const int nb = bin_table(ocw, tab);
     const size_t usable = ctx->smem_optin;
+    const size_t fixed = static_smem_bytes(ocw) + 256;                      // static control blocks + slack
     for (int k = 0; k < nb; k++) {
         size_t per_cta = (228 * 1024 - tab[k].ctas * 1024) / tab[k].ctas;   // 1 KB reserved per resident CTA
-        per_cta = std::min(per_cta, usable) - 12288;                        // static control blocks + slack
+        per_cta = std::min(per_cta, usable) - fixed;
         B.grp_bytes[k] = (int64_t)((per_cta / tab[k].groups) & ~(size_t)15);
     }
     // two passes (count, then fill) over the host copy of the last pivots
