@@ -227,7 +227,7 @@ struct Ctl {
 // executed by all of the group's threads.  Geometry and climb state are read from / written to the
 // control block inside the leader-only sections, so the compute loop keeps only the chip pixels,
 // the tile pointer and the pitch in registers.
-template <int OCW, int G, typename CtlT>
+template <int OCW, int G, bool EXACTP, typename CtlT>
 __device__ __forceinline__ void node_rounds(const Match2Args &a, CtlT &ctl, float *sa, const float (&chip)[Cfg<OCW, G>::L],
                                             const int pitch, const int r, const int col0, const bool active, const int t,
                                             const int lane, const int gwarp) {
@@ -384,6 +384,23 @@ __device__ __forceinline__ void node_rounds(const Match2Args &a, CtlT &ctl, floa
                         float acc0 = a.A0, acc1 = a.A0, lo0 = a.Mlo, lo1 = a.Mlo;
 #pragma unroll
                         for (int k = 0; k < L; k++) {
+                            if (EXACTP) {
+                                // every product is exact in FP32 (scaled operands < 2^12): fma(r, s, acc) ==
+                                // fadd(acc, fmul(r, s)) and fma(r, s, -z) == p - z, one instruction less per pixel
+                                const float rv = chip[k], sv = sp[k];
+                                if (k & 1) {
+                                    const float s1 = __fmaf_rn(rv, sv, acc1);
+                                    const float z = __fsub_rn(s1, acc1);
+                                    lo1 = __fadd_rn(lo1, __fmaf_rn(rv, sv, -z));
+                                    acc1 = s1;
+                                } else {
+                                    const float s1 = __fmaf_rn(rv, sv, acc0);
+                                    const float z = __fsub_rn(s1, acc0);
+                                    lo0 = __fadd_rn(lo0, __fmaf_rn(rv, sv, -z));
+                                    acc0 = s1;
+                                }
+                                continue;
+                            }
                             const float p = __fmul_rn(chip[k], sp[k]);
                             if (k & 1) {
                                 const float s1 = __fadd_rn(acc1, p);
@@ -533,7 +550,7 @@ __device__ __forceinline__ void node_rounds(const Match2Args &a, CtlT &ctl, floa
     }
 }
 
-template <int OCW, int G>
+template <int OCW, int G, bool EXACTP>
 __global__ void __launch_bounds__(kThreads, min_ctas(OCW)) match2_kernel(const Match2Args a) {
     using C = Cfg<OCW, G>;
     constexpr int S = C::S, L = C::L;
@@ -675,7 +692,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(OCW)) match2_kernel(const M
         }
         PROF_T(t_stage1);
         PROF_ADD(1, t_stage1 - t_node0);
-        node_rounds<OCW, G>(a, ctl, sa, chip, pitch, r, col0, active, t, lane, gwarp);
+        node_rounds<OCW, G, EXACTP>(a, ctl, sa, chip, pitch, r, col0, active, t, lane, gwarp);
         PROF_T(t_node1);
         PROF_ADD(0, t_node1 - t_node0);
         PROF_ADD(6, 1);
@@ -688,9 +705,9 @@ float min_dn_float() {
     return f;
 }
 
-template <int OCW, int G>
+template <int OCW, int G, bool EXACTP>
 int launch_one(mimc3cu_ctx *ctx, Match2Args &a, int groups_per_cta, size_t smem, int n_list, long long *grid_out) {
-    auto kern = match2_kernel<OCW, G>;
+    auto kern = match2_kernel<OCW, G, EXACTP>;
     const int threads = G * groups_per_cta;   // <= kThreads; the kernel only needs whole groups
     CU_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -738,10 +755,10 @@ static size_t static_smem_bytes(int ocw) {
     cudaFuncAttributes fa;
     cudaError_t e = cudaErrorInvalidValue;
     switch (ocw) {
-        case 7: e = cudaFuncGetAttributes(&fa, match2_kernel<7, 32>); break;
-        case 15: e = cudaFuncGetAttributes(&fa, match2_kernel<15, 32>); break;
-        case 30: e = cudaFuncGetAttributes(&fa, match2_kernel<30, 256>); break;
-        case 40: e = cudaFuncGetAttributes(&fa, match2_kernel<40, 256>); break;
+        case 7: e = cudaFuncGetAttributes(&fa, match2_kernel<7, 32, false>); break;
+        case 15: e = cudaFuncGetAttributes(&fa, match2_kernel<15, 32, false>); break;
+        case 30: e = cudaFuncGetAttributes(&fa, match2_kernel<30, 256, false>); break;
+        case 40: e = cudaFuncGetAttributes(&fa, match2_kernel<40, 256, false>); break;
     }
     return e == cudaSuccess ? fa.sharedSizeBytes : 12288;
 }
@@ -830,6 +847,8 @@ int launch_match2(mimc3cu_ctx *ctx, const MatchLaunch &L, const Image *ref, cons
     }
     BinCfg tab[kMaxBins];
     const int nb = bin_table(L.ocw, tab);
+    // products of the scaled operands below 2^24 are exact in FP32: the FFMA form of the inner loop applies
+    const bool exactp = b + ref->frac_bits + srch->frac_bits <= 24;
     for (int k = 0; k < nb; k++) {
         if (B->count[k] == 0) continue;
         a.node_list = B->lists + B->start[k]; a.n_list = B->count[k];
@@ -839,10 +858,14 @@ int launch_match2(mimc3cu_ctx *ctx, const MatchLaunch &L, const Image *ref, cons
         const size_t smem = (size_t)a.grp_bytes * tab[k].groups;
         int rc = 0;
         switch (L.ocw) {
-            case 7: rc = launch_one<7, 32>(ctx, a, tab[k].groups, smem, a.n_list, nullptr); break;
-            case 15: rc = launch_one<15, 32>(ctx, a, tab[k].groups, smem, a.n_list, nullptr); break;
-            case 30: rc = launch_one<30, 256>(ctx, a, tab[k].groups, smem, a.n_list, nullptr); break;
-            case 40: rc = launch_one<40, 256>(ctx, a, tab[k].groups, smem, a.n_list, nullptr); break;
+            case 7: rc = exactp ? launch_one<7, 32, true>(ctx, a, tab[k].groups, smem, a.n_list, nullptr)
+                                : launch_one<7, 32, false>(ctx, a, tab[k].groups, smem, a.n_list, nullptr); break;
+            case 15: rc = exactp ? launch_one<15, 32, true>(ctx, a, tab[k].groups, smem, a.n_list, nullptr)
+                                : launch_one<15, 32, false>(ctx, a, tab[k].groups, smem, a.n_list, nullptr); break;
+            case 30: rc = exactp ? launch_one<30, 256, true>(ctx, a, tab[k].groups, smem, a.n_list, nullptr)
+                                : launch_one<30, 256, false>(ctx, a, tab[k].groups, smem, a.n_list, nullptr); break;
+            case 40: rc = exactp ? launch_one<40, 256, true>(ctx, a, tab[k].groups, smem, a.n_list, nullptr)
+                                : launch_one<40, 256, false>(ctx, a, tab[k].groups, smem, a.n_list, nullptr); break;
             default: return mimc3cu_fail(ctx, "match2: unsupported ocw %d", L.ocw);
         }
         if (rc) return rc;
