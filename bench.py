@@ -51,6 +51,10 @@ WORKLOADS = {
     # configs[0]
     "c1": dict(H=2048, W=2048, dtype="u8", spacing=19, mpp=15.0, peak_px=6.3,
                desc="2048x2048 u8 synthetic pair, 100x100-node grid"),
+    # configs[4]: the 32768^2 mosaic at 8-px node spacing (16.7 M nodes on ONE GPU here; with --gpus N every
+    # rank takes one such tile only if memory allows -- meant as a single-GPU maximum-size run)
+    "c5": dict(H=32768, W=32768, dtype="u8", spacing=8, mpp=15.0, peak_px=6.3,
+               desc="32768x32768 u8 synthetic mosaic, 8-px node spacing"),
     # configs[3] (fast outlet glacier), reduced image so it stays a quick extra
     "c4": dict(H=8192, W=8192, dtype="u16", spacing=20, mpp=15.0, peak_px=43.0, apriori_gain=0.9, decorrelated_patches=200,
                band_width_frac=0.2, desc="fast-glacier case: ~43 px a-priori displacement, wide DLC windows, 8192x8192 u16"),
