@@ -168,3 +168,37 @@ def test_find_ncc_peak_batch_cp_shape(gpu_ctx, orc):
             uvo, pko, nco = orc.find_ncc_peak(chips[k], sas[k], piv)
             assert np.array_equal(pk[k], pko) and nc[k] == nco
             assert same_bits_nan_aware(uv[k], uvo), (ocw, k, uv[k], uvo)
+
+
+@pytest.mark.parametrize("matcher", MATCHERS)
+def test_ragged_and_empty_pivot_lists(gpu_ctx, orc, matcher):
+    """Ragged CSR: nodes with 0 pivots (undefined behaviour in the reference, MIMC_module.c:589-591;
+    defined as "nothing evaluable": NaN, NaN, -2), with a single pivot, and with long lists, in one call;
+    also a one-node grid."""
+    sc = small_scene(seed=47, null_wedge=False)
+    i0, i1 = sc.i0.numpy(), sc.i1.numpy()
+    H, W = i0.shape
+    p = lib.params_for(sc.xyuvav, sc.dimx, sc.dimy, sc.dt)
+    off, piv = lib.get_uv_pivot(sc.xyuvav, sc.dt, p.mpp, 15, H, W)
+    # rebuild the CSR: every 5th node loses all pivots, every 7th keeps only the first
+    lists = [piv[off[g]:off[g + 1]] for g in range(sc.n)]
+    for g in range(sc.n):
+        if g % 5 == 0:
+            lists[g] = lists[g][:0]
+        elif g % 7 == 0:
+            lists[g] = lists[g][:1]
+    off2 = np.zeros(sc.n + 1, np.int32); off2[1:] = np.cumsum([len(l) for l in lists])
+    piv2 = np.concatenate([l for l in lists if len(l)]).astype(np.int32)
+    for xy, o, pv in ((sc.xyuvav, off2, piv2), (sc.xyuvav[37:38], np.array([0, len(lists[37])], np.int32), lists[37].astype(np.int32))):
+        gpu_ctx.set_nodes(xy); gpu_ctx.set_pivots(0, o, pv)
+        a, b = gpu_ctx.image_from(i0), gpu_ctx.image_from(i1)
+        gpu_ctx.set_matcher(matcher)
+        try:
+            dp, peak, ncell = gpu_ctx.match(a, b, np.array(sc.offset, np.int32), 0, +1, 15)
+        finally:
+            gpu_ctx.set_matcher("auto")
+            gpu_ctx.image_destroy(a); gpu_ctx.image_destroy(b)
+        dpo, peako, ncello = orc.match(i0, i1, xy, np.array(sc.offset, np.int32), o, pv, +1, 15)
+        _assert_parity((dp, peak, ncell), (dpo, peako, ncello), f"ragged {matcher} n={len(xy)}")
+        empty = np.diff(o) == 0
+        assert (dp[empty, 2] == -2).all() and np.isnan(dp[empty, 0]).all()
