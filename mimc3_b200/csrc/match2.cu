@@ -84,12 +84,12 @@ struct Sums {
 // Resident CTAs per SM each instantiation is compiled for (register cap = 65536 / (256 * n)) and
 // that the first shared-memory bin is sized for: ocw 40 keeps 27 chip pixels per thread (80
 // registers, 3 CTAs), ocw 30 keeps 16 (64 registers, 4 CTAs); measured on B200 (profiles/).
-constexpr int min_ctas(int ocw) { return ocw == 15 ? 2 : (ocw == 30 ? 5 : 4); }
+constexpr int min_ctas(int ocw, int G) { return G == 256 && ocw < 30 ? 6 : (ocw == 15 ? 2 : (ocw == 30 ? 5 : 4)); }
 
 template <int OCW, int G>
 struct Cfg {
     static constexpr int S = 2 * OCW + 1;
-    static constexpr int NSEG = G / S;
+    static constexpr int NSEG = (G / S) < S ? (G / S) : S;   // row segments per chip row (at most one pixel each)
     static constexpr int L = (S + NSEG - 1) / NSEG;
     static constexpr int NGROUPS = kThreads / G;
     static constexpr int NWARPS = G / 32;
@@ -551,7 +551,7 @@ __device__ __forceinline__ void node_rounds(const Match2Args &a, CtlT &ctl, floa
 }
 
 template <int OCW, int G, bool EXACTP>
-__global__ void __launch_bounds__(kThreads, min_ctas(OCW)) match2_kernel(const Match2Args a) {
+__global__ void __launch_bounds__(kThreads, min_ctas(OCW, G)) match2_kernel(const Match2Args a) {
     using C = Cfg<OCW, G>;
     constexpr int S = C::S, L = C::L;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -729,12 +729,16 @@ inline int group_size(int ocw) { return ocw >= 30 ? 256 : 32; }
 // `ctas` CTAs fit on an SM.  A node goes to the first bin it fits; the warp-per-node kernels get
 // two extra bins with few warps per CTA so that wide search areas (fast glaciers) stay on this
 // kernel instead of falling back to the general FP64 one.
-struct BinCfg { int groups, ctas; };
+struct BinCfg { int G, groups, ctas; };
 constexpr int kMaxBins = 5;
 inline int bin_table(int ocw, BinCfg *t) {
-    if (ocw == 30) { t[0] = {1, 5}; t[1] = {1, 4}; t[2] = {1, 3}; t[3] = {1, 2}; t[4] = {1, 1}; return 5; }
-    if (ocw >= 30) { t[0] = {1, 4}; t[1] = {1, 3}; t[2] = {1, 2}; t[3] = {1, 1}; return 4; }
-    t[0] = {8, ocw == 7 ? 4 : 2}; t[1] = {8, 2}; t[2] = {8, 1}; t[3] = {2, 2}; t[4] = {1, 1};
+    if (ocw == 30) { t[0] = {256, 1, 5}; t[1] = {256, 1, 4}; t[2] = {256, 1, 3}; t[3] = {256, 1, 2}; t[4] = {256, 1, 1}; return 5; }
+    if (ocw >= 30) { t[0] = {256, 1, 4}; t[1] = {256, 1, 3}; t[2] = {256, 1, 2}; t[3] = {256, 1, 1}; return 4; }
+    // small chips: a warp per node while eight nodes (one CTA) fit on an SM; nodes with very wide search
+    // areas (fast ice) would leave the SM with one or two warps that way, so they get a whole
+    // 256-thread CTA each (row segments of <= 4 pixels per thread): more instructions per cell, but
+    // many more resident warps (measured: +10 % on the fast-glacier workload, a loss for moderate areas)
+    t[0] = {32, 8, ocw == 7 ? 4 : 2}; t[1] = {32, 8, 2}; t[2] = {32, 8, 1}; t[3] = {256, 1, 3}; t[4] = {256, 1, 1};
     return 5;
 }
 
@@ -751,12 +755,12 @@ bool match2_supported(const MatchLaunch &L, const Image *ref, const Image *srch)
     return b + ref->frac_bits + srch->frac_bits <= 37;
 }
 
-static size_t static_smem_bytes(int ocw) {
+static size_t static_smem_bytes(int ocw, int G) {
     cudaFuncAttributes fa;
     cudaError_t e = cudaErrorInvalidValue;
     switch (ocw) {
-        case 7: e = cudaFuncGetAttributes(&fa, match2_kernel<7, 32, false>); break;
-        case 15: e = cudaFuncGetAttributes(&fa, match2_kernel<15, 32, false>); break;
+        case 7: e = G == 256 ? cudaFuncGetAttributes(&fa, match2_kernel<7, 256, false>) : cudaFuncGetAttributes(&fa, match2_kernel<7, 32, false>); break;
+        case 15: e = G == 256 ? cudaFuncGetAttributes(&fa, match2_kernel<15, 256, false>) : cudaFuncGetAttributes(&fa, match2_kernel<15, 32, false>); break;
         case 30: e = cudaFuncGetAttributes(&fa, match2_kernel<30, 256, false>); break;
         case 40: e = cudaFuncGetAttributes(&fa, match2_kernel<40, 256, false>); break;
     }
@@ -767,10 +771,11 @@ static void build_bins(mimc3cu_ctx *ctx, PivotSet *ps, PivotSet::Bins &B, int oc
     BinCfg tab[kMaxBins];
     const int nb = bin_table(ocw, tab);
     const size_t usable = ctx->smem_optin;
-    const size_t fixed = static_smem_bytes(ocw) + 256;                      // static control blocks + slack
+    const size_t fixed = static_smem_bytes(ocw, group_size(ocw)) + 256;     // static control blocks + slack
+    const size_t fixed256 = static_smem_bytes(ocw, 256) + 256;
     for (int k = 0; k < nb; k++) {
         size_t per_cta = (228 * 1024 - tab[k].ctas * 1024) / tab[k].ctas;   // 1 KB reserved per resident CTA
-        per_cta = std::min(per_cta, usable) - fixed;
+        per_cta = std::min(per_cta, usable) - (tab[k].G == 256 ? fixed256 : fixed);
         B.grp_bytes[k] = (int64_t)((per_cta / tab[k].groups) & ~(size_t)15);
     }
     // two passes (count, then fill) over the host copy of the last pivots
@@ -858,10 +863,14 @@ int launch_match2(mimc3cu_ctx *ctx, const MatchLaunch &L, const Image *ref, cons
         const size_t smem = (size_t)a.grp_bytes * tab[k].groups;
         int rc = 0;
         switch (L.ocw) {
-            case 7: rc = exactp ? launch_one<7, 32, true>(ctx, a, tab[k].groups, smem, a.n_list, nullptr)
-                                : launch_one<7, 32, false>(ctx, a, tab[k].groups, smem, a.n_list, nullptr); break;
-            case 15: rc = exactp ? launch_one<15, 32, true>(ctx, a, tab[k].groups, smem, a.n_list, nullptr)
-                                : launch_one<15, 32, false>(ctx, a, tab[k].groups, smem, a.n_list, nullptr); break;
+            case 7:
+                if (tab[k].G == 256) rc = exactp ? launch_one<7, 256, true>(ctx, a, 1, smem, a.n_list, nullptr) : launch_one<7, 256, false>(ctx, a, 1, smem, a.n_list, nullptr);
+                else rc = exactp ? launch_one<7, 32, true>(ctx, a, tab[k].groups, smem, a.n_list, nullptr) : launch_one<7, 32, false>(ctx, a, tab[k].groups, smem, a.n_list, nullptr);
+                break;
+            case 15:
+                if (tab[k].G == 256) rc = exactp ? launch_one<15, 256, true>(ctx, a, 1, smem, a.n_list, nullptr) : launch_one<15, 256, false>(ctx, a, 1, smem, a.n_list, nullptr);
+                else rc = exactp ? launch_one<15, 32, true>(ctx, a, tab[k].groups, smem, a.n_list, nullptr) : launch_one<15, 32, false>(ctx, a, tab[k].groups, smem, a.n_list, nullptr);
+                break;
             case 30: rc = exactp ? launch_one<30, 256, true>(ctx, a, tab[k].groups, smem, a.n_list, nullptr)
                                 : launch_one<30, 256, false>(ctx, a, tab[k].groups, smem, a.n_list, nullptr); break;
             case 40: rc = exactp ? launch_one<40, 256, true>(ctx, a, tab[k].groups, smem, a.n_list, nullptr)
