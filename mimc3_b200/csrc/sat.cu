@@ -153,7 +153,15 @@ int ensure_image_sat(mimc3cu_ctx *ctx, Image *im) {
     if (im->sat_valid) return 0;
     const int H = im->H, W = im->W, W1 = W + 1;
     const size_t elems = (size_t)(H + 1) * W1;
-    if (!im->sat) CU_CHECK(ctx, cudaMalloc(&im->sat, elems * sizeof(ulonglong2)));
+    if (!im->sat) {
+        // 16 B per pixel; if HBM cannot hold it the image simply stays on the general FP64 matcher
+        if (cudaMalloc(&im->sat, elems * sizeof(ulonglong2)) != cudaSuccess) {
+            cudaGetLastError();
+            im->sat = nullptr;
+            im->exact_class = false;
+            return 0;
+        }
+    }
     const int R = 128, nchunks = (H + R - 1) / R;
     if (int rc = ensure_scratch(ctx, (size_t)nchunks * W1 * sizeof(ulonglong2))) return rc;
     ulonglong2 *tot = (ulonglong2 *)ctx->scratch;
