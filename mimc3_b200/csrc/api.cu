@@ -275,18 +275,36 @@ int mimc3cu_conv2(mimc3cu_ctx *ctx, int32_t src, const float *kernel, int32_t kh
 int64_t mimc3cu_get_uv_pivot(const double *xyuvav, int32_t n, float dt, float mpp, float AW_SF, float AW_CRE, int32_t ocw,
                              int32_t H, int32_t W, int32_t *off, int32_t *piv) {
     if (!xyuvav || !off || n < 0) { mimc3cu_fail(nullptr, "get_uv_pivot: bad arguments"); return -1; }
-    std::vector<int32_t> cnt((size_t)n);
-    parallel_for(n, [&](int32_t b, int32_t e) {
-        for (int32_t g = b; g < e; g++) cnt[g] = pivot_step(xyuvav + 6 * (size_t)g, dt, mpp, AW_SF, AW_CRE, ocw, H, W).count;
-    });
+    // The two-call protocol (sizes first, then the pivots) would evaluate the trigonometry three
+    // times per node; the steps of the sizing call are kept for the immediately following fill call.
+    struct Cache {
+        const double *xy = nullptr; int32_t n = 0, ocw = 0, H = 0, W = 0; float dt = 0, mpp = 0, sf = 0, cre = 0;
+        double first_row[6] = {0, 0, 0, 0, 0, 0};
+        std::vector<PivotStep> steps;
+    };
+    static thread_local Cache cache;
+    const bool hit = piv && cache.xy == xyuvav && cache.n == n && cache.ocw == ocw && cache.H == H && cache.W == W &&
+                     cache.dt == dt && cache.mpp == mpp && cache.sf == AW_SF && cache.cre == AW_CRE && n > 0 &&
+                     memcmp(cache.first_row, xyuvav, sizeof(cache.first_row)) == 0 && cache.steps.size() == (size_t)n;
+    if (!hit) {
+        cache.steps.resize((size_t)n);
+        PivotStep *out = cache.steps.data();   // NOT `cache` inside the workers: it is thread_local
+        parallel_for(n, [&, out](int32_t b, int32_t e) {
+            for (int32_t g = b; g < e; g++) out[g] = pivot_step(xyuvav + 6 * (size_t)g, dt, mpp, AW_SF, AW_CRE, ocw, H, W);
+        });
+        cache.xy = xyuvav; cache.n = n; cache.ocw = ocw; cache.H = H; cache.W = W;
+        cache.dt = dt; cache.mpp = mpp; cache.sf = AW_SF; cache.cre = AW_CRE;
+        if (n > 0) memcpy(cache.first_row, xyuvav, sizeof(cache.first_row));
+    }
+    const PivotStep *steps = cache.steps.data();
     int64_t tot = 0;
-    for (int32_t g = 0; g < n; g++) { off[g] = (int32_t)tot; tot += cnt[g]; }
-    off[n] = (int32_t)tot;
+    for (int32_t g = 0; g < n; g++) { off[g] = (int32_t)tot; tot += steps[g].count; }
     if (tot > 0x7fffffffLL) { mimc3cu_fail(nullptr, "get_uv_pivot: more than 2^31 pivots"); return -1; }
+    off[n] = (int32_t)tot;
     if (!piv) return tot;
-    parallel_for(n, [&](int32_t b, int32_t e) {
+    parallel_for(n, [&, steps](int32_t b, int32_t e) {
         for (int32_t g = b; g < e; g++) {
-            PivotStep s = pivot_step(xyuvav + 6 * (size_t)g, dt, mpp, AW_SF, AW_CRE, ocw, H, W);
+            const PivotStep s = steps[g];
             int32_t *dst = piv + 2 * (size_t)off[g];
             float u = 0.0f, v = 0.0f;
             if (s.count > 0) { dst[0] = 0; dst[1] = 0; }
@@ -297,6 +315,7 @@ int64_t mimc3cu_get_uv_pivot(const double *xyuvav, int32_t n, float dt, float mp
             }
         }
     });
+    cache.xy = nullptr;   // one-shot: the host array may be rewritten before the next call
     return tot;
 }
 

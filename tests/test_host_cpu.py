@@ -80,3 +80,20 @@ def test_product_package_does_not_import_the_oracle():
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", txt, flags=re.M), os.path.join(dirpath, f)
                 assert "mimc3_oracle" not in txt, os.path.join(dirpath, f)
+
+
+def test_get_uv_pivot_multithreaded_grid(orc):
+    """Grids of >= 4096 nodes take the library's multi-threaded path (and its sizing/fill cache)."""
+    from mimc3_b200 import synth
+    sc = synth.make_scene(H=1536, W=1536, dtype="u8", spacing=19, seed=3, peak_px=9.0)
+    assert sc.n >= 4096
+    p = lib.params_for(sc.xyuvav, sc.dimx, sc.dimy, sc.dt)
+    for ocw in (7, 40):
+        off, piv = lib.get_uv_pivot(sc.xyuvav, sc.dt, p.mpp, ocw, 1536, 1536)
+        off_o, piv_o = orc.get_uv_pivot(sc.xyuvav, sc.dt, p.mpp, ocw, 1536, 1536)
+        assert np.array_equal(off, off_o) and np.array_equal(piv, piv_o)
+    # a modified copy of the same array object must not hit the cache of the previous call
+    x2 = sc.xyuvav.copy(); x2[:, 4] *= 3.0
+    off2, piv2 = lib.get_uv_pivot(x2, sc.dt, p.mpp, 40, 1536, 1536)
+    off2_o, piv2_o = orc.get_uv_pivot(x2, sc.dt, p.mpp, 40, 1536, 1536)
+    assert np.array_equal(off2, off2_o) and np.array_equal(piv2, piv2_o)
