@@ -48,6 +48,12 @@ def build(force: bool = False) -> None:
     subprocess.run(args, check=True, stdout=subprocess.DEVNULL)
 
 
+class CpParams(C.Structure):
+    """orc_cp_params: the control-point constants of MIMC_main.c:134-168."""
+    _fields_ = [("vec_ocw", C.c_int32 * 4), ("AW_CRE", C.c_float), ("num_cp_max", C.c_int32), ("num_cp_min", C.c_int32),
+                ("ratio_cp", C.c_float), ("thres_spd_cp", C.c_float)]
+
+
 class PostParams(C.Structure):
     _fields_ = [("dt", C.c_float), ("mpp", C.c_float), ("meter_per_spacing", C.c_float),
                 ("radius_neighbor_dpf1", C.c_float), ("radius_neighbor_ps", C.c_float),
@@ -99,6 +105,9 @@ class Oracle:
         L.orc_finalize.restype = None
         L.orc_finalize.argtypes = [_f32p, C.POINTER(PostParams), C.POINTER(C.c_float), C.POINTER(C.c_float)]
         L.orc_num_threads.restype = C.c_int
+        L.orc_get_offset_image.restype = C.c_int
+        L.orc_get_offset_image.argtypes = [_f32p, _f32p, C.c_int32, C.c_int32, _f64p, C.c_int32, C.POINTER(CpParams), C.c_uint,
+                                           _i32p, _u8p]
 
     def num_threads(self) -> int:
         return int(self.lib.orc_num_threads())
@@ -132,6 +141,14 @@ class Oracle:
         uv = np.zeros(3, np.float32); pk = np.zeros(2, np.int32); nc = np.zeros(1, np.int32)
         self.lib.orc_find_ncc_peak(r, r.shape[0], s, s.shape[0], s.shape[1], p, p.shape[0], uv, pk, nc)
         return uv, pk, int(nc[0])
+
+    def get_offset_image(self, i0, i1, xyuvav, seed):
+        """get_offset_image (MIMC_module.c:33-492) with the reference's constants -> (rc, offset, flag_cp)."""
+        i0 = _as(i0, np.float32); i1 = _as(i1, np.float32); x = _as(xyuvav, np.float64)
+        p = CpParams((C.c_int32 * 4)(*VEC_OCW), AW_CRE, 500, 50, 0.03, 10.0)
+        off = np.zeros(2, np.int32); flag = np.zeros(x.shape[0], np.uint8)
+        rc = self.lib.orc_get_offset_image(i0, i1, i0.shape[0], i0.shape[1], x, x.shape[0], C.byref(p), int(seed) & 0xffffffff, off, flag)
+        return rc, off, flag
 
     def conv2(self, img, kernel_id, out):
         """In place on `out` (float32 (H,W)), like main's reused i0c/i1c buffers."""

@@ -627,3 +627,146 @@ void orc_finalize(float *planes, const orc_post_params *p, float *du_cp_out, flo
     if (du_cp_out) *du_cp_out = du_cp;
     if (dv_cp_out) *dv_cp_out = dv_cp;
 }
+
+/* --------------------------------------------------------------------------------- */
+/* get_offset_image :33-492, GMA_double_randperm_row :494-540                          */
+/* --------------------------------------------------------------------------------- */
+static float img_at(const float *img, int32_t H, int32_t W, int32_t v, int32_t u) {
+    /* the reference does no bounds check here (:100-103, :264, :288); outside pixels read as 0 */
+    return (u >= 0 && u < W && v >= 0 && v < H) ? img[(size_t)v * W + u] : 0.0f;
+}
+
+int orc_get_offset_image(const float *i0, const float *i1, int32_t H, int32_t W, const double *xyuvav, int32_t n,
+                         const orc_cp_params *p, unsigned int seed, int32_t *offset, uint8_t *flag_cp) {
+    static const float K0[3] = {-1, 0, 1}, K1[3] = {-1, 0, 1};                  /* MIMC_main.c:175-196 */
+    static const float K2[9] = {-0.125f, -0.125f, -0.125f, -0.125f, 1.0f, -0.125f, -0.125f, -0.125f, -0.125f};
+    const float *kern[3] = {K0, K1, K2};
+    const int kh[3] = {1, 3, 3}, kw[3] = {3, 1, 3};
+    const int32_t ocw2 = p->vec_ocw[2];
+    const int32_t ocw_chip = (int32_t)(ocw2 + p->AW_CRE + 2);                    /* :48 */
+    const int32_t T = 2 * ocw_chip + 1, Tw = T + 2;
+    int32_t num_cp;
+    if (n * p->ratio_cp > p->num_cp_max) num_cp = p->num_cp_max;                 /* :57-64 */
+    else num_cp = (int32_t)(n * p->ratio_cp);
+
+    /* candidates :71-121 */
+    int32_t *cand = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n > 0 ? n : 1));
+    int32_t num_cand = 0;
+    const int32_t thres_numpx = (ocw2 * 2 + 1) * (ocw2 * 2 + 1) / 2;
+    for (int32_t g = 0; g < n; g++) {
+        float spd_sq = xyuvav[6 * (size_t)g + 4] * xyuvav[6 * (size_t)g + 4] + xyuvav[6 * (size_t)g + 5] * xyuvav[6 * (size_t)g + 5];
+        if (!(spd_sq < p->thres_spd_cp * p->thres_spd_cp)) continue;
+        int32_t u = (int32_t)xyuvav[6 * (size_t)g + 2], v = (int32_t)xyuvav[6 * (size_t)g + 3];
+        int32_t inv0 = 0;
+        for (int32_t c1 = -ocw2; c1 <= ocw2; c1++)
+            for (int32_t c2 = -ocw2; c2 <= ocw2; c2++) {
+                int32_t vv = c1 + v, uu = c2 + u;
+                if (uu >= 0 && uu < W && vv >= 0 && vv < H && i0[(size_t)vv * W + uu] < 0.00001) inv0++;
+            }
+        if (inv0 > thres_numpx) continue;                                        /* :111 (tests i0 twice) */
+        cand[num_cand++] = g;
+    }
+    if (num_cand < p->num_cp_min) { free(cand); return -1; }                     /* :130-135 */
+    if (num_cp > num_cand) num_cp = (int32_t)((float)num_cand * 0.75);           /* :137-141 */
+    if (num_cp < 1) num_cp = 1;                                                  /* (the reference divides by zero here) */
+
+    /* GMA_double_randperm_row :494-540 on the candidate rows */
+    {
+        int32_t *tmp = (int32_t *)malloc(sizeof(int32_t) * (size_t)num_cand), *out = (int32_t *)malloc(sizeof(int32_t) * (size_t)num_cand);
+        memcpy(tmp, cand, sizeof(int32_t) * (size_t)num_cand);
+        srand(seed);                                                             /* :516 */
+        for (int32_t lim = num_cand - 1; lim >= 0; lim--) {
+            int32_t idx = lim != 0 ? (int32_t)(rand() % lim) : 0;
+            out[lim] = tmp[idx]; tmp[idx] = tmp[0]; tmp[0] = tmp[lim];           /* :531-537 */
+        }
+        memcpy(cand, out, sizeof(int32_t) * (size_t)num_cand);
+        free(tmp); free(out);
+    }
+    int32_t num_segment = (num_cand < p->num_cp_min) ? 1 : num_cand / num_cp;   /* :186 */
+    int32_t *seg = (int32_t *)malloc(sizeof(int32_t) * (size_t)(num_segment + 1));
+    seg[0] = 0;
+    for (int32_t c = 1; c <= num_segment; c++) seg[c] = (int32_t)(num_cand * ((float)c / (float)num_segment));   /* :193 */
+
+    /* shared rectangular pivot set :165-176 */
+    const int32_t R = (int32_t)p->AW_CRE, P = (2 * R + 1) * (2 * R + 1);
+    int32_t *piv = (int32_t *)malloc(sizeof(int32_t) * 2 * (size_t)P);
+    { int32_t k = 0; for (int32_t a = -R; a <= R; a++) for (int32_t b = -R; b <= R; b++) { piv[2 * k] = a; piv[2 * k + 1] = b; k++; } }
+
+    float sduv[2] = {0.0f, 0.0f};
+    int32_t num_cp_current = 0, ok = 0;
+    for (int32_t c = 0; c < num_segment; c++) {
+        const int32_t nsub = seg[c + 1] - seg[c];
+        if (nsub <= 0) continue;
+        float *dp = (float *)calloc((size_t)16 * nsub * 3, sizeof(float));
+        float *tile0 = (float *)malloc(sizeof(float) * (size_t)nsub * T * T), *tile1 = (float *)malloc(sizeof(float) * (size_t)nsub * T * T);
+        for (int variant = -1; variant <= 2; variant++) {                        /* :248 */
+            /* ONE output buffer per image, reused for every node of the segment (:273-276): the
+             * stale-border behaviour of GMA_float_conv2 chains the nodes together */
+            float *tin = (float *)calloc((size_t)Tw * Tw, sizeof(float));
+            float *out0 = (float *)calloc((size_t)Tw * Tw, sizeof(float)), *out1 = (float *)calloc((size_t)Tw * Tw, sizeof(float));
+            for (int32_t k = 0; k < nsub; k++) {
+                const int32_t g = cand[seg[c] + k];
+                const int32_t u = (int32_t)xyuvav[6 * (size_t)g + 2], v = (int32_t)xyuvav[6 * (size_t)g + 3];
+                for (int im = 0; im < 2; im++) {
+                    const float *img = im ? i1 : i0;
+                    float *tile = (im ? tile1 : tile0) + (size_t)k * T * T;
+                    if (variant < 0) {                                           /* :250-268 */
+                        for (int32_t a = -ocw_chip; a <= ocw_chip; a++)
+                            for (int32_t b = -ocw_chip; b <= ocw_chip; b++)
+                                tile[(size_t)(a + ocw_chip) * T + (b + ocw_chip)] = img_at(img, H, W, v + a, u + b);
+                    } else {                                                     /* :273-308 */
+                        float *out = im ? out1 : out0;
+                        for (int32_t a = -ocw_chip - 1; a <= ocw_chip + 1; a++)
+                            for (int32_t b = -ocw_chip - 1; b <= ocw_chip + 1; b++)
+                                tin[(size_t)(a + ocw_chip + 1) * Tw + (b + ocw_chip + 1)] = img_at(img, H, W, v + a, u + b);
+                        orc_conv2(tin, Tw, Tw, kern[variant], kh[variant], kw[variant], out);
+                        for (int32_t a = 0; a < T; a++)
+                            for (int32_t b = 0; b < T; b++) tile[(size_t)a * T + b] = out[(size_t)(a + 1) * Tw + (b + 1)];
+                    }
+                }
+            }
+            free(tin); free(out0); free(out1);
+            for (int c3 = 1; c3 < 3; c3++) {                                     /* :325 */
+                const int32_t ocw = p->vec_ocw[c3], S = 2 * ocw + 1;
+                const int32_t slot = (c3 - 1) * 8 + (variant + 1) * 2;
+#pragma omp parallel
+                {
+                    float *chip = (float *)malloc(sizeof(float) * (size_t)S * S);
+#pragma omp for schedule(dynamic)
+                    for (int32_t k = 0; k < nsub; k++) {
+                        for (int dir = 0; dir < 2; dir++) {
+                            const float *rt = (dir ? tile1 : tile0) + (size_t)k * T * T, *st = (dir ? tile0 : tile1) + (size_t)k * T * T;
+                            for (int32_t a = -ocw; a <= ocw; a++)
+                                for (int32_t b = -ocw; b <= ocw; b++)
+                                    chip[(size_t)(a + ocw) * S + (b + ocw)] = rt[(size_t)(ocw_chip + a) * T + (ocw_chip + b)];
+                            float uvncc[3];
+                            orc_find_ncc_peak(chip, S, st, T, T, piv, P, uvncc, NULL, NULL);     /* :351, :369 */
+                            float *d = dp + ((size_t)(slot + dir) * nsub + k) * 3;
+                            d[0] = dir ? -uvncc[0] : uvncc[0]; d[1] = dir ? -uvncc[1] : uvncc[1]; d[2] = uvncc[2];
+                        }
+                    }
+                    free(chip);
+                }
+            }
+        }
+        float *mvn = (float *)calloc((size_t)nsub * 16 * 5, sizeof(float));
+        int32_t *ncl = (int32_t *)calloc((size_t)nsub, sizeof(int32_t));
+        orc_cluster(dp, nsub, 16, mvn, ncl);                                     /* :389 */
+        for (int32_t k = 0; k < nsub; k++)
+            for (int32_t q = 0; q < ncl[k]; q++)
+                if (mvn[((size_t)k * 16 + q) * 5 + 4] >= 0.6) {                  /* :400 */
+                    sduv[0] += mvn[((size_t)k * 16 + q) * 5]; sduv[1] += mvn[((size_t)k * 16 + q) * 5 + 1];
+                    flag_cp[cand[seg[c] + k]] = 1;
+                    num_cp_current++;
+                }
+        free(mvn); free(ncl); free(dp); free(tile0); free(tile1);
+        if (num_cp <= num_cp_current) { ok = 1; break; }                         /* :419 */
+    }
+    free(seg); free(piv); free(cand);
+    if (!ok && num_cp_current >= p->num_cp_min) ok = 1;                          /* :437-441 */
+    if (!ok) return -1;
+    float du_cp = sduv[0] / (float)num_cp_current, dv_cp = sduv[1] / (float)num_cp_current;
+    offset[0] = du_cp > 0 ? (int32_t)(du_cp + 0.5) : (int32_t)(du_cp - 0.5);    /* :455-473 */
+    offset[1] = dv_cp > 0 ? (int32_t)(dv_cp + 0.5) : (int32_t)(dv_cp - 0.5);
+    return 1;
+}

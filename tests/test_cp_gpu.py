@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
     (1234567, dict(H=640, W=900, seed=62, spacing=17, null_wedge=False, offset=(-3, 4))),
     (42, dict(H=700, W=700, seed=63, spacing=23, null_wedge=True, dtype="u16", offset=(5, 2))),
 ])
-def test_get_offset_image_matches_reference(gpu_ctx, ref, seed_time, scene_kw):
+def test_get_offset_image_matches_reference(gpu_ctx, ref, orc, seed_time, scene_kw):
     sc = small_scene(**scene_kw)
     i0, i1 = sc.i0.numpy(), sc.i1.numpy()
     ref.set_globals(sc.xyuvav, sc.dimx, sc.dimy, sc.dt)
@@ -30,6 +30,8 @@ def test_get_offset_image_matches_reference(gpu_ctx, ref, seed_time, scene_kw):
     assert np.array_equal(off, np.array(sc.offset, np.int32))          # and it is the true rigid offset
     assert np.array_equal(flag, flag_r), f"{(flag != flag_r).sum()} control-point flags differ"
     assert ncp >= flag.sum() > 0
+    rc_o, off_o, flag_o = orc.get_offset_image(i0, i1, sc.xyuvav, seed_time)          # and the restated oracle
+    assert rc_o == 1 and np.array_equal(off_o, off) and np.array_equal(flag_o, flag)
 
 
 def test_get_offset_image_fails_without_candidates(gpu_ctx):

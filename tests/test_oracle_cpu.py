@@ -117,3 +117,18 @@ def test_oracle_equals_reference_build_live(orc, ref):
             dpo, _, _ = orc.match(a, b, sc.xyuvav, o, off, piv, sign, ocw)
             dpr, _ = ref.match(a, b, sc.xyuvav, o, off, sign * piv, +1, ocw)
             assert same_bits_nan_aware(dpo, dpr), f"ocw {ocw} sign {sign}: " + mismatch_report(dpo, dpr)
+
+
+@pytest.mark.parametrize("seed_time", (1700000000, 99))
+def test_control_point_stage_equals_reference(orc, ref, seed_time):
+    """get_offset_image (candidates, glibc-rand permutation, segments, tile-local conv2 on a reused
+    output buffer, 16 attempts, clusters): same return code, offset and CP flags as the reference
+    build with time() pinned to the seed."""
+    sc = small_scene(H=600, W=600, seed=81, spacing=22, null_wedge=True, offset=(-2, 3))
+    i0, i1 = sc.i0.numpy(), sc.i1.numpy()
+    ref.set_globals(sc.xyuvav, sc.dimx, sc.dimy, sc.dt)
+    rc_r, off_r, flag_r = ref.get_offset_image(i0, i1, sc.xyuvav, fake_time=seed_time)
+    rc, off, flag = orc.get_offset_image(i0, i1, sc.xyuvav, seed_time)
+    assert rc == rc_r == 1
+    assert np.array_equal(off, off_r) and np.array_equal(off, np.array(sc.offset, np.int32))
+    assert np.array_equal(flag, flag_r) and flag.sum() > 0
