@@ -386,7 +386,7 @@ __device__ __forceinline__ void node_rounds(const Match2Args &a, CtlT &ctl, floa
                     const int cy = job >> 16, cx = job & 0xffff;
                     unsigned int hi = 0;
                     int lo = 0;
-                    if (active) {
+                    {   // threads without chip pixels (r = col0 = 0, chip all zero) run the same code: no branch
                         const float *sp = sa + (cy + 1 + r) * pitch + (cx + 1 + col0);
                         float acc0 = a.A0, acc1 = a.A0, lo0 = a.Mlo, lo1 = a.Mlo;
 #pragma unroll
@@ -699,7 +699,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(OCW, G)) match2_kernel(cons
         }
         PROF_T(t_stage1);
         PROF_ADD(1, t_stage1 - t_node0);
-        node_rounds<OCW, G, EXACTP>(a, ctl, sa, chip, pitch, r, col0, active, t, lane, gwarp);
+        node_rounds<OCW, G, EXACTP>(a, ctl, sa, chip, pitch, active ? r : 0, active ? col0 : 0, active, t, lane, gwarp);
         PROF_T(t_node1);
         PROF_ADD(0, t_node1 - t_node0);
         PROF_ADD(6, 1);
