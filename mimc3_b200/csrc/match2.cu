@@ -235,8 +235,8 @@ struct Ctl {
 // control block inside the leader-only sections, so the compute loop keeps only the chip pixels,
 // the tile pointer and the pitch in registers.
 template <int OCW, int G, bool EXACTP, typename CtlT>
-__device__ __forceinline__ void node_rounds(const Match2Args &a, CtlT &ctl, float *sa, const float (&chip)[Cfg<OCW, G>::L],
-                                            const int pitch, const int r, const int col0, const bool active, const int t,
+__device__ __forceinline__ void node_rounds(const Match2Args &a, CtlT &ctl, float *sa, const float *sa_thread,
+                                            const float (&chip)[Cfg<OCW, G>::L], const int pitch, const bool active, const int t,
                                             const int lane, const int gwarp) {
     using C = Cfg<OCW, G>;
     constexpr int S = C::S, L = C::L;
@@ -387,7 +387,7 @@ __device__ __forceinline__ void node_rounds(const Match2Args &a, CtlT &ctl, floa
                     unsigned int hi = 0;
                     int lo = 0;
                     {   // threads without chip pixels (r = col0 = 0, chip all zero) run the same code: no branch
-                        const float *sp = sa + (cy + 1 + r) * pitch + (cx + 1 + col0);
+                        const float *sp = sa_thread + (cy + 1) * pitch + (cx + 1);
                         float acc0 = a.A0, acc1 = a.A0, lo0 = a.Mlo, lo1 = a.Mlo;
 #pragma unroll
                         for (int k = 0; k < L; k++) {
@@ -491,7 +491,7 @@ __device__ __forceinline__ void node_rounds(const Match2Args &a, CtlT &ctl, floa
                     const int cell = cy * ctl.geo.cw + cx;
                     Sums s = {0.0, 0.0, 0.0, 0.0, 0.0, 0};
                     if (active) {
-                        const float *sp = sa + (cy + 1 + r) * pitch + (cx + 1 + col0);
+                        const float *sp = sa_thread + (cy + 1) * pitch + (cx + 1);
 #pragma unroll
                         for (int k = 0; k < L; k++) {
                             const float rv = chip[k], sv = sp[k];
@@ -699,7 +699,8 @@ __global__ void __launch_bounds__(kThreads, min_ctas(OCW, G)) match2_kernel(cons
         }
         PROF_T(t_stage1);
         PROF_ADD(1, t_stage1 - t_node0);
-        node_rounds<OCW, G, EXACTP>(a, ctl, sa, chip, pitch, active ? r : 0, active ? col0 : 0, active, t, lane, gwarp);
+        // this thread's view of the tile: row r, first column col0 (threads without chip pixels: the origin)
+        node_rounds<OCW, G, EXACTP>(a, ctl, sa, sa + (active ? r * pitch + col0 : 0), chip, pitch, active, t, lane, gwarp);
         PROF_T(t_node1);
         PROF_ADD(0, t_node1 - t_node0);
         PROF_ADD(6, 1);
