@@ -407,8 +407,7 @@ def main():
 
         def e2e_step():
             pl.set_images(i0_host, i1_host)                              # H2D + on-device cast
-            pl.set_grid(xy_host, sc.dimx, sc.dimy, sc.dt)                # nodes + host pivots + H2D
-            d, _ = pl.multimatch(offset)
+            d, _ = pl.match_all(xy_host, sc.dimx, sc.dimy, sc.dt, offset)   # nodes + host pivots + H2D overlapped with the attempts
             if world == 1:
                 pln, _ = pl.postprocess(d)
                 ctx.finalize(pln, pl.params)

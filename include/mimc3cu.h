@@ -85,6 +85,8 @@ int mimc3cu_image_upload_u16(mimc3cu_ctx *ctx, int32_t handle, const uint16_t *h
 /* Device -> device copy from a caller-owned device buffer (e.g. a torch tensor). */
 int mimc3cu_image_copy_from_device(mimc3cu_ctx *ctx, int32_t handle, const float *dev);
 int mimc3cu_image_download(mimc3cu_ctx *ctx, int32_t handle, float *host);
+/* Zero the payload (asynchronous on the context stream). */
+int mimc3cu_image_fill_zero(mimc3cu_ctx *ctx, int32_t handle);
 /* Raw device pointer of the image payload. */
 float *mimc3cu_image_ptr(mimc3cu_ctx *ctx, int32_t handle);
 

@@ -172,6 +172,7 @@ void mimc3cu_destroy(mimc3cu_ctx *ctx) {
         if (p.off) cudaFree(p.off);
         if (p.piv) cudaFree(p.piv);
         for (auto &b : p.bins) if (b.lists) cudaFree(b.lists);
+        if (p.last_use) cudaEventDestroy(p.last_use);
     }
     if (ctx->statbuf) cudaFree(ctx->statbuf);
     if (ctx->overflow_list) cudaFree(ctx->overflow_list);
@@ -252,6 +253,14 @@ int mimc3cu_image_download(mimc3cu_ctx *ctx, int32_t handle, float *host) {
     if (!im) return mimc3cu_fail(ctx, "image_download: bad handle %d", handle);
     CU_CHECK(ctx, cudaMemcpyAsync(host, im->d, (size_t)im->H * im->W * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int mimc3cu_image_fill_zero(mimc3cu_ctx *ctx, int32_t handle) {
+    Image *im = get_image(ctx, handle);
+    if (!im) return mimc3cu_fail(ctx, "image_fill_zero: bad handle %d", handle);
+    image_invalidate(im);
+    CU_CHECK(ctx, cudaMemsetAsync(im->d, 0, (size_t)im->H * im->W * sizeof(float), ctx->stream));
     return 0;
 }
 
@@ -345,8 +354,10 @@ int mimc3cu_set_pivots(mimc3cu_ctx *ctx, int32_t slot, const int32_t *off, const
     if (slot < 0 || slot >= MIMC3CU_MAX_PIVOT_SLOTS) return mimc3cu_fail(ctx, "set_pivots: bad slot %d", slot);
     if (n <= 0) return mimc3cu_fail(ctx, "set_pivots: n must be positive");
     CU_CHECK(ctx, cudaSetDevice(ctx->device));
-    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     PivotSet &ps = ctx->pivots[slot];
+    // Only launches that read THIS slot have to finish: the host can prepare the pivots of the next chip
+    // size while the GPU is still matching with the previous one (mimc3_b200/pipeline.py does).
+    if (ps.last_use) CU_CHECK(ctx, cudaEventSynchronize(ps.last_use));
     for (auto &b : ps.bins) b.ocw = -1;   // node lists are rebuilt lazily (their device buffers are reused)
     ps.n = n; ps.total = off[n];
     ps.last_u.assign((size_t)n, 0); ps.last_v.assign((size_t)n, 0);
@@ -415,8 +426,16 @@ int mimc3cu_match_async(mimc3cu_ctx *ctx, int32_t ref_img, int32_t search_img, c
                                      "chip size is outside its class");
     }
     ctx->last_matcher = v2 ? 2 : 1;
-    ScopedTimer tm(ctx, 0);
-    return v2 ? launch_match2(ctx, L, r, s, &ps) : launch_match(ctx, L);
+    int rc;
+    {
+        ScopedTimer tm(ctx, 0);
+        rc = v2 ? launch_match2(ctx, L, r, s, &ps) : launch_match(ctx, L);
+    }
+    if (!rc) {
+        if (!ps.last_use) CU_CHECK(ctx, cudaEventCreateWithFlags(&ps.last_use, cudaEventDisableTiming));
+        CU_CHECK(ctx, cudaEventRecord(ps.last_use, ctx->stream));
+    }
+    return rc;
 }
 
 int mimc3cu_set_matcher(mimc3cu_ctx *ctx, int32_t mode) {

@@ -30,6 +30,8 @@ struct PivotSet {
     int32_t n = 0;
     int64_t total = 0;
     size_t off_cap = 0, piv_cap = 0;        // device capacities (elements), reused across set_pivots calls
+    cudaEvent_t last_use = nullptr;         // recorded after every matcher launch that reads this slot: replacing the
+                                            // slot only waits for those launches, not for the whole stream
     int32_t max_abs_u = 0, max_abs_v = 0;   // over the last pivot of every node
     int64_t max_cells = 0;                  // max (2|ul|+4)(2|vl|+4): reachable cmap region
     int64_t max_sarea_extra = 0;            // helper: max over nodes of (|ul|+2, |vl|+2) product terms

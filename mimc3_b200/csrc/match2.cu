@@ -820,7 +820,9 @@ int launch_match2(mimc3cu_ctx *ctx, const MatchLaunch &L, const Image *ref, cons
     for (auto &b : ps->bins) if (b.ocw == L.ocw) B = &b;
     if (!B) {
         B = ps->bins[0].ocw < 0 ? &ps->bins[0] : &ps->bins[1];
-        CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+        // no launch that reads this slot's node lists can be in flight: set_pivots waited for them, and a second
+        // chip size on the same slot uses the other cache entry (a third one recycles: wait for the slot then)
+        if (B->ocw >= 0 && ps->last_use) CU_CHECK(ctx, cudaEventSynchronize(ps->last_use));
         build_bins(ctx, ps, *B, L.ocw);
     }
     if (ctx->overflow_cap < (size_t)L.n) {

@@ -58,6 +58,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "mimc3cu_image_upload_u16": (C.c_int, [vp, i32, vp]),
         "mimc3cu_image_copy_from_device": (C.c_int, [vp, i32, vp]),
         "mimc3cu_image_download": (C.c_int, [vp, i32, vp]),
+        "mimc3cu_image_fill_zero": (C.c_int, [vp, i32]),
         "mimc3cu_image_ptr": (vp, [vp, i32]),
         "mimc3cu_conv2": (C.c_int, [vp, i32, vp, i32, i32, i32]),
         "mimc3cu_get_uv_pivot": (i64, [vp, i32, f32, f32, f32, f32, i32, i32, i32, vp, vp]),
@@ -105,7 +106,7 @@ EXPORTED_SYMBOLS = (
     "mimc3cu_postprocess_stage", "mimc3cu_finalize", "mimc3cu_fp32_peak", "mimc3cu_timing_enable",
     "mimc3cu_timing_read", "mimc3cu_malloc", "mimc3cu_free", "mimc3cu_memcpy_d2h",
     "mimc3cu_memcpy_h2d", "mimc3cu_set_matcher", "mimc3cu_last_matcher", "mimc3cu_image_class",
-    "mimc3cu_get_offset_image", "mimc3cu_band_halo", "mimc3cu_postprocess_band",
+    "mimc3cu_get_offset_image", "mimc3cu_band_halo", "mimc3cu_postprocess_band", "mimc3cu_image_fill_zero",
 )
 
 
@@ -226,6 +227,9 @@ class Context:
         else:
             self.image_upload(h, arr.numpy())
         return h
+
+    def image_fill_zero(self, handle):
+        self._ck(self.L.mimc3cu_image_fill_zero(self.h, handle))
 
     def image_download(self, handle, H, W) -> np.ndarray:
         out = np.empty((H, W), np.float32)

@@ -11,6 +11,12 @@ import torch
 from . import lib
 
 VEC_OCW = (7, 15, 30, 40)   # MIMC_main.c:134-137
+# the three filter kernels the driver builds at MIMC_main.c:175-196 (d/dx, d/dy, Laplacian)
+FILTERS = (
+    np.array([[-1, 0, 1]], dtype=np.float32),
+    np.array([[-1], [0], [1]], dtype=np.float32),
+    np.array([[-0.125, -0.125, -0.125], [-0.125, 1.0, -0.125], [-0.125, -0.125, -0.125]], dtype=np.float32),
+)
 
 
 class Pipeline:
@@ -60,7 +66,44 @@ class Pipeline:
             self.ctx.set_pivots(slot, off, piv)
             self.pivot_bytes += off.nbytes + piv.nbytes
 
-    # ---- compute --------------------------------------------------------------------------------
+    def match_all(self, xyuvav, dimx, dimy, dt, offset, want_ncell=False):
+        """set_grid + multimatch with the host work hidden behind the GPU: the pivots of chip size k+1
+        are generated (host threads) and uploaded while the GPU runs the raw-pair attempts of chip size k;
+        the filtered variants follow.  Same launches in the same stream order, hence the same results, as
+        ``set_grid(); multimatch()`` (MIMC_main.c:261-350) -> dp (32, n, 3) on the device."""
+        x = np.ascontiguousarray(xyuvav, dtype=np.float64)
+        self.params = lib.params_for(x, dimx, dimy, dt)
+        self.xyuvav = x
+        self.n = n = x.shape[0]
+        self.ctx.set_nodes(x)
+        off_f = np.ascontiguousarray(offset, dtype=np.int32)
+        off_r = -off_f
+        dp = torch.empty((32, n, 3), dtype=torch.float32, device=self.device)
+        ncell = torch.empty((32, n), dtype=torch.int32, device=self.device) if want_ncell else None
+        h = self.handles
+        self.pivot_bytes = 0
+
+        def attempts(variant, slot, a, b):
+            ocw = VEC_OCW[slot]
+            idx = variant * 8 + slot * 2        # dp[cnt*2] / dp[cnt*8+cntc*2+8], MIMC_main.c:267-349
+            self.ctx.match_async(a, b, off_f, slot, +1, ocw, False, dp[idx], None, ncell[idx] if want_ncell else None)
+            self.ctx.match_async(b, a, off_r, slot, -1, ocw, True, dp[idx + 1], None, ncell[idx + 1] if want_ncell else None)
+
+        for slot, ocw in enumerate(VEC_OCW):     # raw pair; pivots generated just in time
+            off, piv = lib.get_uv_pivot(x, dt, self.params.mpp, ocw, self.H, self.W, self.params.AW_SF, self.params.AW_CRE)
+            self.ctx.set_pivots(slot, off, piv)
+            self.pivot_bytes += off.nbytes + piv.nbytes
+            attempts(0, slot, h["i0"], h["i1"])
+        # main allocates i0c/i1c once (zeros under the zero-initialised-allocation semantics, SURVEY.md H1)
+        self.ctx.image_fill_zero(h["i0c"])
+        self.ctx.image_fill_zero(h["i1c"])
+        for k in range(3):
+            self.ctx.conv2(h["i0"], FILTERS[k], h["i0c"])
+            self.ctx.conv2(h["i1"], FILTERS[k], h["i1c"])
+            for slot in range(4):
+                attempts(k + 1, slot, h["i0c"], h["i1c"])
+        return dp, ncell
+
     def multimatch(self, offset, want_ncell=False):
         """All 32 attempts (MIMC_main.c:261-350) -> dp (32, n, 3) on the device."""
         dp = torch.empty((32, self.n, 3), dtype=torch.float32, device=self.device)
@@ -88,8 +131,7 @@ class Pipeline:
     def run(self, i0, i1, xyuvav, dimx, dimy, dt, offset, finalize=True):
         """End to end from host buffers to the five host planes (+ CP sub-pixel bias)."""
         self.set_images(i0, i1)
-        self.set_grid(xyuvav, dimx, dimy, dt)
-        dp, _ = self.multimatch(offset)
+        dp, _ = self.match_all(xyuvav, dimx, dimy, dt, offset)
         planes, stats = self.postprocess(dp)
         bias = (0.0, 0.0)
         if finalize:

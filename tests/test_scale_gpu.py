@@ -78,3 +78,24 @@ def test_swapped_pass_mirrors_forward_pass_for_identical_images(gpu_ctx, big):
         assert np.allclose(df[inner, 2], 1.0, atol=1e-6) and np.allclose(ds[inner, 2], 1.0, atol=1e-6)
     finally:
         gpu_ctx.image_destroy(a); gpu_ctx.image_destroy(b)
+
+
+def test_overlapped_flow_equals_the_serial_flow(big):
+    """Pipeline.match_all (pivots of the next chip size generated while the GPU matches the current
+    one; pivot slots re-uploaded while earlier launches may still read them) == set_grid + multimatch."""
+    from mimc3_b200.pipeline import Pipeline
+    sc = big
+    pl = Pipeline(0)
+    try:
+        pl.set_images(sc.i0, sc.i1)
+        pl.set_grid(sc.xyuvav, sc.dimx, sc.dimy, sc.dt)
+        ref, ref_nc = pl.multimatch(sc.offset, want_ncell=True)
+        pl.ctx.sync()
+        ref = ref.cpu().numpy(); ref_nc = ref_nc.cpu().numpy()
+        for _ in range(2):      # second pass overwrites live pivot slots
+            dp, nc = pl.match_all(sc.xyuvav, sc.dimx, sc.dimy, sc.dt, sc.offset, want_ncell=True)
+            pl.ctx.sync()
+            assert np.array_equal(nc.cpu().numpy(), ref_nc)
+            assert same_bits_nan_aware(dp.cpu().numpy(), ref)
+    finally:
+        pl.close()
