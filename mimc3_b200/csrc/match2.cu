@@ -132,6 +132,19 @@ __device__ __forceinline__ void stage_rows(const float *__restrict__ src, int gs
     }
 }
 
+// Packed FP32 pairs (sm_100 FMUL2 / FADD2 / FFMA2): each lane rounds exactly like the scalar instruction.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float x, float y) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float &x, float &y) { asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); }
+// The product is written as fma(x, y, +0): ptxas (12.9) contracts mul.rn.f32x2 + add.rn.f32x2 into one
+// FFMA2 despite the explicit roundings, which would skip the float rounding of the product the reference
+// performs; FFMA2 with RZ as addend is left alone (operands are non-negative, so no signed-zero issue).
+// The u16 parity tests (products beyond 24 bits) fail if a toolchain ever changes this.
+__device__ __forceinline__ f32x2 mul2(f32x2 x, f32x2 y) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(x), "l"(y), "l"(0ull)); return r; }
+__device__ __forceinline__ f32x2 add2(f32x2 x, f32x2 y) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(y)); return r; }
+__device__ __forceinline__ f32x2 sub2(f32x2 x, f32x2 y) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(x), "l"(y)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 x, f32x2 y, f32x2 z) { f32x2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(x), "l"(y), "l"(z)); return r; }
+
 // Order-preserving map float -> uint32 (NaN -> 0), for warp arg-max with REDUX.
 __device__ __forceinline__ unsigned int ordered_key(float v) {
     if (v != v) return 0u;
@@ -388,39 +401,33 @@ __device__ __forceinline__ void node_rounds(const Match2Args &a, CtlT &ctl, floa
                     int lo = 0;
                     {   // threads without chip pixels (r = col0 = 0, chip all zero) run the same code: no branch
                         const float *sp = sa_thread + (cy + 1) * pitch + (cx + 1);
-                        float acc0 = a.A0, acc1 = a.A0, lo0 = a.Mlo, lo1 = a.Mlo;
+                        // Two pixels per instruction (FMUL2 / FADD2 / FFMA2, sm_100): lane 0 of the packed pair
+                        // accumulates the even pixels, lane 1 the odd ones -- the same two accumulators as a
+                        // scalar loop would keep, at half the issue slots.
+                        f32x2 acc = pack2(a.A0, a.A0), lo2 = pack2(a.Mlo, a.Mlo);
 #pragma unroll
-                        for (int k = 0; k < L; k++) {
+                        for (int k = 0; k < L; k += 2) {
+                            // an odd L ends with a (pixel, 0) pair: the zero is a literal, not a load
+                            const f32x2 rv = pack2(chip[k], k + 1 < L ? chip[k + 1] : 0.0f);
+                            const f32x2 sv = pack2(sp[k], k + 1 < L ? sp[k + 1] : 0.0f);
                             if (EXACTP) {
                                 // every product is exact in FP32 (scaled operands < 2^12): fma(r, s, acc) ==
                                 // fadd(acc, fmul(r, s)) and fma(r, s, -z) == p - z, one instruction less per pixel
-                                const float rv = chip[k], sv = sp[k];
-                                if (k & 1) {
-                                    const float s1 = __fmaf_rn(rv, sv, acc1);
-                                    const float z = __fsub_rn(s1, acc1);
-                                    lo1 = __fadd_rn(lo1, __fmaf_rn(rv, sv, -z));
-                                    acc1 = s1;
-                                } else {
-                                    const float s1 = __fmaf_rn(rv, sv, acc0);
-                                    const float z = __fsub_rn(s1, acc0);
-                                    lo0 = __fadd_rn(lo0, __fmaf_rn(rv, sv, -z));
-                                    acc0 = s1;
-                                }
-                                continue;
-                            }
-                            const float p = __fmul_rn(chip[k], sp[k]);
-                            if (k & 1) {
-                                const float s1 = __fadd_rn(acc1, p);
-                                const float z = __fsub_rn(s1, acc1);
-                                lo1 = __fadd_rn(lo1, __fsub_rn(p, z));
-                                acc1 = s1;
+                                const f32x2 s1 = fma2(rv, sv, acc);
+                                const f32x2 nz = sub2(acc, s1);
+                                lo2 = add2(lo2, fma2(rv, sv, nz));
+                                acc = s1;
                             } else {
-                                const float s1 = __fadd_rn(acc0, p);
-                                const float z = __fsub_rn(s1, acc0);
-                                lo0 = __fadd_rn(lo0, __fsub_rn(p, z));
-                                acc0 = s1;
+                                const f32x2 pr = mul2(rv, sv);
+                                const f32x2 s1 = add2(acc, pr);
+                                const f32x2 z = sub2(s1, acc);
+                                lo2 = add2(lo2, sub2(pr, z));
+                                acc = s1;
                             }
                         }
+                        float acc0, acc1, lo0, lo1;
+                        unpack2(acc, acc0, acc1);
+                        unpack2(lo2, lo0, lo1);
                         hi = (__float_as_uint(acc0) - a.A0_bits) + (__float_as_uint(acc1) - a.A0_bits);
                         lo = (int)(__float_as_uint(lo0) - a.Mlo_bits) + (int)(__float_as_uint(lo1) - a.Mlo_bits);
                     }

@@ -20,6 +20,13 @@ __global__ void __launch_bounds__(256) k(uint32_t *out, uint32_t seed, float fa,
     __syncthreads();
 #pragma unroll
     for (int c = 0; c < CHAINS; c++) { x[c] = threadIdx.x * 7 + c + seed; f[c] = (float)x[c]; d[c] = (double)x[c]; w[c] = x[c]; }
+    unsigned long long wa;
+    asm volatile("mov.b64 %0, {%1, %1};" : "=l"(wa) : "f"(fa));
+    if (OP >= 24) {
+#pragma unroll
+        for (int c = 0; c < CHAINS; c++) asm volatile("mov.b64 %0, {%1, %2};" : "=l"(w[c]) : "f"(f[c]), "f"(f[(c + 3) % CHAINS]));
+    }
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(&sm[(threadIdx.x * 9) & 1023]) & ~7u;
     for (int it = 0; it < ITERS; it++) {
 #pragma unroll
         for (int c = 0; c < CHAINS; c++) {
@@ -47,6 +54,46 @@ __global__ void __launch_bounds__(256) k(uint32_t *out, uint32_t seed, float fa,
             if (OP == 21) { asm volatile("cvt.rn.f32.s32 %0, %1;" : "=f"(f[c]) : "r"(x[c])); }
             if (OP == 22) { unsigned long long t; asm volatile("cvt.rzi.s64.f32 %0, %1;" : "=l"(t) : "f"(f[c])); w[c] += t; }
             if (OP == 23) { asm volatile("popc.b32 %0, %0;" : "+r"(x[c])); }
+            // packed FP32 (sm_100+): two lanes of FP32 per 64-bit register pair
+            if (OP == 24) asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(w[c]) : "l"(w[(c + 1) % CHAINS]));
+            if (OP == 25) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(w[c]) : "l"(wa), "l"(w[(c + 1) % CHAINS]));
+            if (OP == 26) asm volatile("mul.rn.f32x2 %0, %0, %1;" : "+l"(w[c]) : "l"(wa));
+            // the matcher's inner loop per pixel: LDS + FMUL + Fast2Sum (4 FADD), scalar ...
+            if (OP == 27) {
+                float sv, p, t, z, e;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(sv) : "r"(sbase + c * 4));
+                asm volatile("mul.rn.f32 %0, %1, %2;" : "=f"(p) : "f"(fa), "f"(sv));
+                asm volatile("add.rn.f32 %0, %1, %2;" : "=f"(t) : "f"(f[c & 1]), "f"(p));
+                asm volatile("sub.rn.f32 %0, %1, %2;" : "=f"(z) : "f"(t), "f"(f[c & 1]));
+                asm volatile("sub.rn.f32 %0, %1, %2;" : "=f"(e) : "f"(p), "f"(z));
+                asm volatile("add.rn.f32 %0, %0, %1;" : "+f"(f[2 + (c & 1)]) : "f"(e));
+                f[c & 1] = t;
+            }
+            // ... and packed, two pixels per instruction (two LDS.32 into a register pair)
+            if (OP == 28 && (c & 1) == 0) {
+                unsigned long long sv, p, t, z, e;
+                float s0, s1;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(s0) : "r"(sbase + c * 4));
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(s1) : "r"(sbase + c * 4 + 4));
+                asm volatile("mov.b64 %0, {%1, %2};" : "=l"(sv) : "f"(s0), "f"(s1));
+                asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(p) : "l"(wa), "l"(sv));
+                asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(w[(c >> 1) & 1]), "l"(p));
+                asm volatile("sub.rn.f32x2 %0, %1, %2;" : "=l"(z) : "l"(t), "l"(w[(c >> 1) & 1]));
+                asm volatile("sub.rn.f32x2 %0, %1, %2;" : "=l"(e) : "l"(p), "l"(z));
+                asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(w[2 + ((c >> 1) & 1)]) : "l"(e));
+                w[(c >> 1) & 1] = t;
+            }
+            // same with one LDS.64 per pixel pair
+            if (OP == 29 && (c & 1) == 0) {
+                unsigned long long sv, p, t, z, e;
+                asm volatile("ld.shared.b64 %0, [%1];" : "=l"(sv) : "r"(sbase + c * 4));
+                asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(p) : "l"(wa), "l"(sv));
+                asm volatile("add.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(w[(c >> 1) & 1]), "l"(p));
+                asm volatile("sub.rn.f32x2 %0, %1, %2;" : "=l"(z) : "l"(t), "l"(w[(c >> 1) & 1]));
+                asm volatile("sub.rn.f32x2 %0, %1, %2;" : "=l"(e) : "l"(p), "l"(z));
+                asm volatile("add.rn.f32x2 %0, %0, %1;" : "+l"(w[2 + ((c >> 1) & 1)]) : "l"(e));
+                w[(c >> 1) & 1] = t;
+            }
         }
     }
     uint32_t acc = 0;
@@ -106,6 +153,14 @@ int main() {
     run<18>("FFMA+LOP3 pair", 2, out, sms, mhz);
     run<19>("IDP4A+FADD pair", 2, out, sms, mhz);
     run<20>("FMUL+F2D+DADD triple", 3, out, sms, mhz);
+    printf("packed FP32: lane-ops count each FP32 lane (2 per instruction)\n");
+    run<24>("FADD2", 2, out, sms, mhz);
+    run<25>("FFMA2", 2, out, sms, mhz);
+    run<26>("FMUL2", 2, out, sms, mhz);
+    printf("matcher inner loop, pixels/clk/SM\n");
+    run<27>("px: LDS+FMUL+4FADD", 1, out, sms, mhz);
+    run<28>("px: 2LDS+FMUL2+4FADD2 (/2px)", 1, out, sms, mhz);
+    run<29>("px: LDS64+FMUL2+4FADD2 (/2px)", 1, out, sms, mhz);
     cudaError_t e = cudaDeviceSynchronize();
     printf("status: %s\n", cudaGetErrorString(e));
     return e != cudaSuccess;
