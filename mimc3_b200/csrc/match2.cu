@@ -44,6 +44,11 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr unsigned char kComputed = 1, kVisible = 2, kListed = 4;
+// job word: cy << 16 | cx; bit 31 marks a speculative cell (evaluated ahead of the reference's order because
+// the climb is about to ask for it; skipped instead of re-evaluated when it would need the masked path)
+constexpr int kSpec = (int)0x80000000;
+__device__ __forceinline__ int job_cy(int job) { return (job >> 16) & 0x7fff; }
+__device__ __forceinline__ int job_cx(int job) { return job & 0xffff; }
 constexpr int kMaxJobsCap = 64;   // upper bound of cells per evaluation round (Cfg::MAXJ is per chip size)
 constexpr int kPivCache = 64;
 
@@ -295,9 +300,58 @@ __device__ __forceinline__ void node_rounds(const Match2Args &a, CtlT &ctl, floa
                             m += __popc(wm);
                             __syncwarp();
                         }
-                        if (m == 0 && ip_batch >= P) phase = 1;
+                        if (m == 0 && ip_batch >= P) phase = 2;
                     }
-                    if (phase == 1) {
+                    if (phase == 2) {
+                        // Second probes of all pivots in one round.  After its first probe every pivot steps to the
+                        // arg-max of its 3x3 (a pure function of the values now in the map) and probes there; one
+                        // pivot after the other that is one small round per pivot.  Here lane i predicts pivot i's
+                        // step and the union of the cells those probes will ask for is evaluated at once.  Only
+                        // the evaluation is moved forward: visibility, counts and the climb itself stay with the
+                        // state machine below, which then finds the cells already computed.
+                        phase = 1;
+                        if (ctl.chip_fast) {
+                            for (int base = 0; base < P && m <= C::MAXJ - 9; base += 32) {
+                                const int i = base + lane;
+                                int ccx = -1, ccy = 0;   // centre of the predicted probe, in cell coordinates
+                                if (i < P) {
+                                    const int2 pv = i < kPivCache ? ctl.pivc[i] : piv[i];
+                                    const int bx = a.sign * pv.x + dx2, by = a.sign * pv.y + dy2;
+                                    if (!(bx - OCW <= 1 || bx + OCW >= Dx2 - 1 || by - OCW <= 1 || by + OCW >= Dy2 - 1)) {
+                                        float top = -2.0f;
+                                        int d0 = 0, d1 = 0;
+                                        const float *cv = cval + (by - OCW - 1) * cw + (bx - OCW - 1);
+#pragma unroll
+                                        for (int k = 0; k < 9; k++) {
+                                            const float v = cv[(k % 3 - 1) * cw + (k / 3 - 1)];
+                                            if (v > top) { top = v; d0 = k / 3 - 1; d1 = k % 3 - 1; }
+                                        }
+                                        const int nx = bx + d0, ny = by + d1;
+                                        if ((d0 | d1) != 0 && !(nx - OCW <= 1 || nx + OCW >= Dx2 - 1 || ny - OCW <= 1 || ny + OCW >= Dy2 - 1)) {
+                                            ccx = nx - OCW - 1; ccy = ny - OCW - 1;
+                                        }
+                                    }
+                                }
+                                // one lane per distinct probe centre
+                                const unsigned int peers = __match_any_sync(0xffffffffu, ccx < 0 ? -1 - lane : ((ccy << 16) | ccx));
+                                const bool owner = ccx >= 0 && (__ffs(peers) - 1) == lane;
+#pragma unroll 1
+                                for (int k = 0; k < 9; k++) {
+                                    const int cy = ccy + (k % 3 - 1), cx = ccx + (k / 3 - 1);
+                                    const bool want = owner && !(cflag[cy * cw + cx] & (kComputed | kListed));
+                                    const unsigned int wm = __ballot_sync(0xffffffffu, want);
+                                    const int pos = m + __popc(wm & ((1u << lane) - 1u));
+                                    if (want && pos < C::MAXJ) {
+                                        ctl.job[pos] = kSpec | (cy << 16) | cx;
+                                        cflag[cy * cw + cx] |= kListed;
+                                    }
+                                    m = min(m + __popc(wm), C::MAXJ);
+                                    __syncwarp();
+                                }
+                            }
+                        }
+                    }
+                    if (phase == 1 && m == 0) {
                         // the reference's state machine, MIMC_module.c:691-753
                         for (;;) {
                             if (!in_pivot) {
@@ -380,7 +434,7 @@ __device__ __forceinline__ void node_rounds(const Match2Args &a, CtlT &ctl, floa
                         const int slot = lane + 32 * h;
                         if (slot < m) {
                             const int job = ctl.job[slot];
-                            const int cy = job >> 16, cx = job & 0xffff;
+                            const int cy = job_cy(job), cx = job_cx(job);
                             const int x0 = cx + 1, y0 = cy + 1;                       // window origin in the search area
                             const int ix0 = su0 - dx2 + x0, iy0 = sv0 - dy2 + y0;     // ... and in the image
                             // The last column / row of the search area is never written by the reference
@@ -396,7 +450,7 @@ __device__ __forceinline__ void node_rounds(const Match2Args &a, CtlT &ctl, floa
                 }
                 for (int c = 0; c < m; c++) {
                     const int job = ctl.job[c];
-                    const int cy = job >> 16, cx = job & 0xffff;
+                    const int cy = job_cy(job), cx = job_cx(job);
                     unsigned int hi = 0;
                     int lo = 0;
                     {   // threads without chip pixels (r = col0 = 0, chip all zero) run the same code: no branch
@@ -453,7 +507,7 @@ __device__ __forceinline__ void node_rounds(const Match2Args &a, CtlT &ctl, floa
                         const int slot = lane + 32 * h;
                         if (slot < m) {
                             jobs[h] = ctl.job[slot];
-                            const int cell = (jobs[h] >> 16) * cw + (jobs[h] & 0xffff);
+                            const int cell = job_cy(jobs[h]) * cw + job_cx(jobs[h]);
                             const int trim = w_flag[h] >> 1;
                             if (ctl.chip_fast && (w_flag[h] & 1) && (w_pk[h] & 0xffffffull) == 0) {
                                 long long hs = 0, ls = 0;
@@ -470,7 +524,7 @@ __device__ __forceinline__ void node_rounds(const Match2Args &a, CtlT &ctl, floa
                                 cval[cell] = ncc_from_sums(s);
                                 cflag[cell] |= kComputed;
                             } else {
-                                slowc[h] = true;
+                                slowc[h] = !(jobs[h] & kSpec);   // a speculative cell is dropped; the climb asks again if it matters
                             }
                         }
                     }
@@ -494,7 +548,7 @@ __device__ __forceinline__ void node_rounds(const Match2Args &a, CtlT &ctl, floa
                 unsigned char *cflag = (unsigned char *)(cval + ctl.geo.cell_elems);
                 for (int c = 0; c < m; c++) {
                     const int job = ctl.job[c];
-                    const int cy = job >> 16, cx = job & 0xffff;
+                    const int cy = job_cy(job), cx = job_cx(job);
                     const int cell = cy * ctl.geo.cw + cx;
                     Sums s = {0.0, 0.0, 0.0, 0.0, 0.0, 0};
                     if (active) {

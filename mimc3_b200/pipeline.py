@@ -117,6 +117,23 @@ class Pipeline:
         stats = self.ctx.postprocess(dp, self.xyuvav, self.params, planes)
         return planes, stats
 
+    def postprocess_from_dump(self, directory, xyuvav, dimx, dimy, dt, finalize=True):
+        """Postprocess-only re-run from the dp_NN.gma dump of an earlier run -- the flow of the reference's
+        MIMC_main_test_postprocessing.c:262-300.  Returns (planes (5, dimy, dimx) host, stats, bias)."""
+        from . import gma
+        dp_host, _ = gma.load_dp(directory)
+        x = np.ascontiguousarray(xyuvav, dtype=np.float64)
+        if dp_host.shape[1] != x.shape[0]:
+            raise ValueError(f"dump holds {dp_host.shape[1]} nodes, xyuvav {x.shape[0]}")
+        self.params = lib.params_for(x, dimx, dimy, dt)
+        self.xyuvav = x
+        self.n = x.shape[0]
+        dp = torch.from_numpy(dp_host).to(self.device)
+        planes, stats = self.postprocess(dp)
+        bias = self.ctx.finalize(planes, self.params) if finalize else (0.0, 0.0)
+        self.ctx.sync()
+        return planes.cpu().numpy(), stats, bias
+
     def postprocess_band(self, dp, xyuvav_global, params_global, own_row0, own_rows, transport):
         """This rank's band of the postprocess; collective over all ranks of ``transport``
         (halo exchange + counter all-reduce per sweep, see bands.py).  Returns (planes (5, own_rows,

@@ -31,6 +31,8 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
+from . import gma
+
 
 @dataclasses.dataclass
 class Scene:
@@ -205,20 +207,11 @@ def make_scene(
 # ---------------------------------------------------------------------------------------
 
 def write_gma(path: str, arr: np.ndarray) -> None:
-    """GMA file = int32 nrows, int32 ncols, row-major payload (GMA.c:319-424)."""
-    a = np.ascontiguousarray(arr)
-    if a.ndim == 1:
-        a = a[None, :]
-    with open(path, "wb") as f:
-        f.write(struct.pack("<ii", a.shape[0], a.shape[1]))
-        f.write(a.tobytes())
+    gma.write(path, arr)
 
 
 def read_gma(path: str, dtype="float32") -> np.ndarray:
-    """Inverse of write_gma (same layout the reference's gma.py:3-21 reads)."""
-    with open(path, "rb") as f:
-        nrows, ncols = struct.unpack("<ii", f.read(8))
-        return np.frombuffer(f.read(), dtype=dtype).reshape(nrows, ncols).copy()
+    return gma.read(path, dtype)
 
 
 def write_tiff(path: str, img: np.ndarray) -> None:

@@ -126,3 +126,24 @@ def test_pipeline_end_to_end_accuracy(orc):
     err = np.hypot(err_u, err_v)
     assert np.nanmedian(err) < 0.05 and np.nanpercentile(err, 95) < 0.25, (np.nanmedian(err), np.nanpercentile(err, 95))
     assert np.isnan(planes[0]).mean() < 0.02
+
+
+def test_postprocess_only_rerun_from_a_dp_dump(scene_and_dp, tmp_path):
+    """dp_NN.gma dump -> reload -> postprocess (the reference's MIMC_main_test_postprocessing.c flow)
+    gives the planes of the in-memory run, bit for bit."""
+    from mimc3_b200 import gma
+    sc, offset, dpo = scene_and_dp
+    pl = pipeline.Pipeline(0)
+    try:
+        pl.set_images(sc.i0.numpy(), sc.i1.numpy())
+        dp, _ = pl.match_all(sc.xyuvav, sc.dimx, sc.dimy, sc.dt, offset)
+        planes, stats = pl.postprocess(dp)
+        bias = pl.ctx.finalize(planes, pl.params)
+        pl.ctx.sync()
+        gma.save_dp(str(tmp_path), dp.cpu().numpy())
+        planes2, stats2, bias2 = pl.postprocess_from_dump(str(tmp_path), sc.xyuvav, sc.dimx, sc.dimy, sc.dt)
+        assert same_bits_nan_aware(planes.cpu().numpy(), planes2) and bias == bias2
+        with pytest.raises(ValueError):
+            pl.postprocess_from_dump(str(tmp_path), sc.xyuvav[:-1], sc.dimx, sc.dimy, sc.dt)
+    finally:
+        pl.close()
