@@ -51,6 +51,9 @@ WORKLOADS = {
     # configs[0]
     "c1": dict(H=2048, W=2048, dtype="u8", spacing=19, mpp=15.0, peak_px=6.3,
                desc="2048x2048 u8 synthetic pair, 100x100-node grid"),
+    # configs[2]: Sentinel-2-like 10 m tile, dense 100 m (10 px) node spacing, all four chip sizes
+    "c3": dict(H=10980, W=10980, dtype="u16", spacing=10, mpp=10.0, peak_px=6.3,
+               desc="Sentinel-2-like 10 m tile, 10980x10980 u16 synthetic, 100 m (10 px) node spacing, multichip"),
     # configs[4]: the 32768^2 mosaic at 8-px node spacing (16.7 M nodes on ONE GPU here; with --gpus N every
     # rank takes one such tile only if memory allows -- meant as a single-GPU maximum-size run)
     "c5": dict(H=32768, W=32768, dtype="u8", spacing=8, mpp=15.0, peak_px=6.3,

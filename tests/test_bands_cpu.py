@@ -13,6 +13,25 @@ import torch.multiprocessing as mp
 from mimc3_b200 import bands
 
 
+def test_bands_balanced_by_pivot_counts():
+    """Rows crossing the fast band carry more DLC pivots, hence more NCC cells: bands cut by that weight are
+    narrower there and their estimated work agrees to within one row."""
+    from mimc3_b200 import lib, synth
+    sc = synth.make_scene(H=1024, W=1024, dtype="u8", spacing=16, seed=11, peak_px=30.0, band_angle_deg=0.0, apriori_gain=0.9)
+    p = lib.params_for(sc.xyuvav, sc.dimx, sc.dimy, sc.dt)
+    offs = [lib.get_uv_pivot(sc.xyuvav, sc.dt, p.mpp, ocw, 1024, 1024)[0] for ocw in (7, 15, 30, 40)]
+    w = bands.row_work(offs, sc.dimx, sc.dimy)
+    assert w.shape == (sc.dimy,) and w.max() > 2.0 * w.min()
+    even = bands.split_rows(sc.dimy, 4, min_rows=5)
+    bal = bands.split_rows(sc.dimy, 4, min_rows=5, weights=w)
+    load = lambda parts: np.array([w[r0:r0 + n].sum() for r0, n in parts])
+    assert sum(n for _, n in bal) == sc.dimy
+    assert load(bal).max() - load(bal).min() <= 2 * w.max()
+    assert load(bal).max() < load(even).max()
+    with pytest.raises(ValueError):
+        bands.row_work([offs[0][:-1]], sc.dimx, sc.dimy)
+
+
 def test_split_rows_covers_and_balances():
     for dimy, world in ((813, 8), (100, 2), (40, 8), (17, 3)):
         parts = bands.split_rows(dimy, world, min_rows=5)

@@ -92,6 +92,19 @@ def test_match_on_filtered_images(gpu_ctx, orc, kid, ocw, matcher):
     _assert_parity(got, want, f"filtered kernel {kid} ocw={ocw} {matcher}")
 
 
+@pytest.mark.parametrize("matcher", MATCHERS)
+def test_match_sentinel2_like_ragged_image(gpu_ctx, orc, matcher):
+    """BASELINE.json configs[2] in small: 10 m pixels, dense 100 m (10 px) node spacing, u16, and an image
+    whose width and height are odd (row pitch not a multiple of 16 bytes, like the 10980-px tiles are not a
+    multiple of 128) -- staging and the summed-area tables must not assume alignment."""
+    sc = small_scene(H=549, W=613, dtype="u16", spacing=10, mpp=10.0, seed=31, null_wedge=True)
+    assert sc.n > 2000
+    i0, i1 = sc.i0.numpy(), sc.i1.numpy()
+    for ocw in VEC_OCW:
+        got, want = _run_both(gpu_ctx, orc, sc, i0, i1, np.array(sc.offset, np.int32), +1, ocw, matcher=matcher)
+        _assert_parity(got, want, f"sentinel2-like ocw={ocw} {matcher}")
+
+
 @pytest.mark.parametrize("kid", (0, 2))
 def test_match_on_filtered_u16_images(gpu_ctx, orc, kid):
     """14-bit DN filtered by d/dx and by the Laplacian (values up to 2^18 in units of 1/8):
