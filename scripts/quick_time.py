@@ -1,11 +1,12 @@
-"""Per-chip-size matcher timing on one GPU (development aid): python scripts/quick_time.py [c1|c2s] [v1|v2]"""
+"""Per-chip-size matcher timing on one GPU (development aid): python scripts/quick_time.py [c1|c2s|c4s] [v1|v2]"""
 import sys, time, numpy as np, torch
 sys.path.insert(0, '/root/repo')
 from mimc3_b200 import lib, synth
 wl = sys.argv[1] if len(sys.argv) > 1 else "c1"
 mode = sys.argv[2] if len(sys.argv) > 2 else "auto"
 ocws = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [7, 15, 30, 40]
-cfg = dict(c1=dict(H=2048, W=2048, dtype="u8", spacing=19), c2s=dict(H=4096, W=4096, dtype="u16", spacing=20))[wl]
+cfg = dict(c1=dict(H=2048, W=2048, dtype="u8", spacing=19), c2s=dict(H=4096, W=4096, dtype="u16", spacing=20),
+           c4s=dict(H=4096, W=4096, dtype="u16", spacing=20, peak_px=43.0, apriori_gain=0.9, band_width_frac=0.2))[wl]
 sc = synth.make_scene(seed=1, device="cuda", **cfg)
 ctx = lib.Context(0)
 ctx.set_matcher(mode)
