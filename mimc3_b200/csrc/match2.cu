@@ -751,13 +751,12 @@ __global__ void __launch_bounds__(kThreads, min_ctas(OCW, G)) match2_kernel(cons
             }
         }
         for (int i = t; i < cw * ch; i += G) cflag[i] = 0;
-        gsync<G>();
-
-        if (t == 0) {
+        if (t == 0) {   // written BEFORE the barrier: the other lanes of warp 0 read both right after it
             ctl.geo = {g, P, su0, sv0, dx2, dy2, Dx2, Dy2, cw, ch, sa_elems, cell_elems, piv};
-            // phase 0: up-front first probes, 1: the climb; nslow: masked-path cells pending in ctl.job[0..nslow)
+            // phase 0: up-front first probes, 2: second probes, 1: the climb; nslow: masked-path cells pending in ctl.job[0..nslow)
             ctl.st = {0, 0, 0, 0, 0, -1, -1, 1, dx2, dy2, 0, 0, 0, -2.0f, -2.0f};
         }
+        gsync<G>();
         PROF_T(t_stage1);
         PROF_ADD(1, t_stage1 - t_node0);
         // this thread's view of the tile: row r, first column col0 (threads without chip pixels: the origin)

@@ -154,6 +154,32 @@ def test_match_fast_glacier_wide_windows(gpu_ctx, orc, matcher):
         _assert_parity(got, want, f"fast glacier ocw={ocw} {matcher}")
 
 
+@pytest.mark.parametrize("angle", (30.0, 120.0, 200.0, 290.0))
+def test_match_flow_into_all_quadrants(gpu_ctx, orc, angle):
+    """Fast flow into each of the four quadrants, forward and swapped pass (pivots negated): the pivot line, hence
+    the part of the search area that is actually visited, sits in every corner of the (symmetric) area."""
+    sc = small_scene(H=760, W=760, seed=37, peak_px=30.0, apriori_gain=0.9, spacing=57, null_wedge=False,
+                     band_width_frac=0.3, band_angle_deg=angle, margin=90)
+    i0, i1 = sc.i0.numpy(), sc.i1.numpy()
+    offset = np.array(sc.offset, np.int32)
+    for ocw in (30, 7):
+        got, want = _run_both(gpu_ctx, orc, sc, i0, i1, offset, +1, ocw)
+        assert want[2].max() > 100
+        _assert_parity(got, want, f"quadrant {angle} fwd ocw={ocw}")
+        got, want = _run_both(gpu_ctx, orc, sc, i1, i0, -offset, -1, ocw)
+        _assert_parity(got, want, f"quadrant {angle} swapped ocw={ocw}")
+
+
+def test_match_long_climbs_from_a_poor_apriori(gpu_ctx, orc):
+    """A-priori velocity far off the truth (half of it, 15 px short): climbs of many steps away from the pivot line."""
+    sc = small_scene(H=760, W=760, seed=39, peak_px=30.0, apriori_gain=0.5, spacing=57, null_wedge=False,
+                     band_width_frac=0.3, band_angle_deg=60.0, margin=90)
+    i0, i1 = sc.i0.numpy(), sc.i1.numpy()
+    for ocw in (40, 15):
+        got, want = _run_both(gpu_ctx, orc, sc, i0, i1, np.array(sc.offset, np.int32), +1, ocw)
+        _assert_parity(got, want, f"long climbs ocw={ocw}")
+
+
 @pytest.mark.parametrize("matcher", MATCHERS)
 def test_match_nodes_at_image_border(gpu_ctx, orc, matcher):
     """Search areas hanging over the image edge are zero-filled (extract_sarea boundary check)."""
