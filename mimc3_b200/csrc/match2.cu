@@ -95,8 +95,10 @@ struct Sums {
 
 // Resident CTAs per SM each instantiation is compiled for (register cap = 65536 / (256 * n)) and
 // that the first shared-memory bin is sized for: ocw 40 keeps 27 chip pixels per thread (80
-// registers, 3 CTAs), ocw 30 keeps 16 (64 registers, 4 CTAs); measured on B200 (profiles/).
-constexpr int min_ctas(int ocw, int G) { return G == 256 && ocw < 30 ? 6 : (ocw == 15 ? 2 : (ocw == 30 ? 5 : 4)); }
+// registers, 3 CTAs), ocw 30 keeps 31 in half-CTA groups; measured on B200 (profiles/).
+// ocw 30 runs two 128-thread groups (two nodes) per CTA, 3 CTAs = 6 nodes per SM; its 256-thread
+// instantiation only serves the wide-search-area bins (<= 2 CTAs per SM).
+constexpr int min_ctas(int ocw, int G) { return G == 256 && ocw < 30 ? 6 : (ocw == 15 ? 2 : (ocw == 30 ? 3 : 4)); }
 
 template <int OCW, int G>
 struct Cfg {
@@ -160,7 +162,8 @@ __device__ __forceinline__ unsigned int ordered_key(float v) {
 template <int G>
 __device__ __forceinline__ void gsync() {
     if (G == 32) __syncwarp();
-    else __syncthreads();
+    else if (G == kThreads) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(1 + (int)(threadIdx.x / G)), "n"(G) : "memory");   // one named barrier per group
 }
 
 __device__ __forceinline__ double warp_sum_d(double v) {
@@ -800,7 +803,9 @@ inline int group_size(int ocw) { return ocw >= 30 ? 256 : 32; }
 struct BinCfg { int G, groups, ctas; };
 constexpr int kMaxBins = 5;
 inline int bin_table(int ocw, BinCfg *t) {
-    if (ocw == 30) { t[0] = {256, 1, 5}; t[1] = {256, 1, 4}; t[2] = {256, 1, 3}; t[3] = {256, 1, 2}; t[4] = {256, 1, 1}; return 5; }
+    // ocw 30: half a CTA per node (chip rows in two 31-pixel segments), 6 or 4 nodes per SM at <= 85 registers
+    // (measured: 8 nodes per SM at 64 registers spill and lose 20 %), then whole CTAs for the wide search areas
+    if (ocw == 30) { t[0] = {128, 2, 3}; t[1] = {128, 2, 2}; t[2] = {256, 1, 2}; t[3] = {256, 1, 1}; return 4; }
     if (ocw >= 30) { t[0] = {256, 1, 4}; t[1] = {256, 1, 3}; t[2] = {256, 1, 2}; t[3] = {256, 1, 1}; return 4; }
     // small chips: a warp per node while eight nodes (one CTA) fit on an SM; nodes with very wide search
     // areas (fast ice) would leave the SM with one or two warps that way, so they get a whole
@@ -829,7 +834,7 @@ static size_t static_smem_bytes(int ocw, int G) {
     switch (ocw) {
         case 7: e = G == 256 ? cudaFuncGetAttributes(&fa, match2_kernel<7, 256, false>) : cudaFuncGetAttributes(&fa, match2_kernel<7, 32, false>); break;
         case 15: e = G == 256 ? cudaFuncGetAttributes(&fa, match2_kernel<15, 256, false>) : cudaFuncGetAttributes(&fa, match2_kernel<15, 32, false>); break;
-        case 30: e = cudaFuncGetAttributes(&fa, match2_kernel<30, 256, false>); break;
+        case 30: e = G == 256 ? cudaFuncGetAttributes(&fa, match2_kernel<30, 256, false>) : cudaFuncGetAttributes(&fa, match2_kernel<30, 128, false>); break;
         case 40: e = cudaFuncGetAttributes(&fa, match2_kernel<40, 256, false>); break;
     }
     return e == cudaSuccess ? fa.sharedSizeBytes : 12288;
@@ -839,11 +844,10 @@ static void build_bins(mimc3cu_ctx *ctx, PivotSet *ps, PivotSet::Bins &B, int oc
     BinCfg tab[kMaxBins];
     const int nb = bin_table(ocw, tab);
     const size_t usable = ctx->smem_optin;
-    const size_t fixed = static_smem_bytes(ocw, group_size(ocw)) + 256;     // static control blocks + slack
-    const size_t fixed256 = static_smem_bytes(ocw, 256) + 256;
     for (int k = 0; k < nb; k++) {
+        const size_t fixed = static_smem_bytes(ocw, tab[k].G) + 256;         // static control blocks + slack
         size_t per_cta = (228 * 1024 - tab[k].ctas * 1024) / tab[k].ctas;   // 1 KB reserved per resident CTA
-        per_cta = std::min(per_cta, usable) - (tab[k].G == 256 ? fixed256 : fixed);
+        per_cta = std::min(per_cta, usable) - fixed;
         B.grp_bytes[k] = (int64_t)((per_cta / tab[k].groups) & ~(size_t)15);
     }
     // two passes (count, then fill) over the host copy of the last pivots
@@ -941,8 +945,10 @@ int launch_match2(mimc3cu_ctx *ctx, const MatchLaunch &L, const Image *ref, cons
                 if (tab[k].G == 256) rc = exactp ? launch_one<15, 256, true>(ctx, a, 1, smem, a.n_list, nullptr) : launch_one<15, 256, false>(ctx, a, 1, smem, a.n_list, nullptr);
                 else rc = exactp ? launch_one<15, 32, true>(ctx, a, tab[k].groups, smem, a.n_list, nullptr) : launch_one<15, 32, false>(ctx, a, tab[k].groups, smem, a.n_list, nullptr);
                 break;
-            case 30: rc = exactp ? launch_one<30, 256, true>(ctx, a, tab[k].groups, smem, a.n_list, nullptr)
-                                : launch_one<30, 256, false>(ctx, a, tab[k].groups, smem, a.n_list, nullptr); break;
+            case 30:
+                if (tab[k].G == 256) rc = exactp ? launch_one<30, 256, true>(ctx, a, 1, smem, a.n_list, nullptr) : launch_one<30, 256, false>(ctx, a, 1, smem, a.n_list, nullptr);
+                else rc = exactp ? launch_one<30, 128, true>(ctx, a, tab[k].groups, smem, a.n_list, nullptr) : launch_one<30, 128, false>(ctx, a, tab[k].groups, smem, a.n_list, nullptr);
+                break;
             case 40: rc = exactp ? launch_one<40, 256, true>(ctx, a, tab[k].groups, smem, a.n_list, nullptr)
                                 : launch_one<40, 256, false>(ctx, a, tab[k].groups, smem, a.n_list, nullptr); break;
             default: return mimc3cu_fail(ctx, "match2: unsupported ocw %d", L.ocw);
