@@ -215,6 +215,10 @@ def main():
 
     if args.impl == "reference" and rank != 0:
         return 0   # rank 0 alone runs the CPU arm
+    if world > 1 and "MIMC3CU_HOST_THREADS" not in os.environ:
+        # the ranks of one box share its host cores for the pivot generation of the end-to-end leg
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+        os.environ["MIMC3CU_HOST_THREADS"] = str(max(1, (os.cpu_count() or 8) // max(1, local_world)))
 
     import torch
     from mimc3_b200 import synth

@@ -92,8 +92,10 @@ inline PivotStep pivot_step(const double *row, float dt, float mpp, float AW_SF,
 
 template <typename F>
 void parallel_for(int32_t n, F f) {
+    // MIMC3CU_HOST_THREADS caps the worker threads (one process per GPU shares the host cores with its siblings)
+    static const int cap = [] { const char *e = getenv("MIMC3CU_HOST_THREADS"); int v = e ? atoi(e) : 0; return v > 0 ? v : 64; }();
     unsigned hw = std::thread::hardware_concurrency();
-    int nt = (int)std::max(1u, std::min(hw ? hw : 4u, 64u));
+    int nt = (int)std::max(1u, std::min(hw ? hw : 4u, (unsigned)cap));
     if (n < 4096) nt = 1;
     if (nt == 1) { f(0, n); return; }
     std::vector<std::thread> th;
