@@ -875,6 +875,11 @@ static void build_bins(mimc3cu_ctx *ctx, PivotSet *ps, PivotSet::Bins &B, int oc
     }
     cudaMemcpy(B.lists, all.data(), sizeof(int32_t) * all.size(), cudaMemcpyHostToDevice);
     B.ocw = ocw;
+    if (getenv("MIMC3CU_DEBUG_BINS")) {
+        fprintf(stderr, "[mimc3cu] ocw %d bins:", ocw);
+        for (int k = 0; k < nb; k++) fprintf(stderr, " {G %d x %d, %d CTA/SM, %lld B/node}: %lld", tab[k].G, tab[k].groups, tab[k].ctas, (long long)B.grp_bytes[k], (long long)cnt[k]);
+        fprintf(stderr, "  general kernel: %lld of %d nodes\n", (long long)cnt[kMaxBins], ps->n);
+    }
 }
 
 int launch_match2(mimc3cu_ctx *ctx, const MatchLaunch &L, const Image *ref, const Image *srch, PivotSet *ps) {

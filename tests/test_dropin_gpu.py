@@ -58,6 +58,11 @@ def test_unchanged_driver_with_the_cuda_module_writes_the_same_files(tmp_path, d
     assert a["meta"]["cp_offset_int_v"] == b["meta"]["cp_offset_int_v"] == str(sc.offset[1])
     assert np.array_equal(a["x"], b["x"]) and np.array_equal(a["y"], b["y"])
     assert np.array_equal(a["flagcp"], b["flagcp"])
+    # the reader tooling (mimc3_b200/vmap.py) on files written by the reference's own savers
+    from mimc3_b200 import vmap
+    vm = vmap.VMap(os.path.join(work, "out_ref"))
+    assert np.array_equal(vm.vx, a["vx"], equal_nan=True) and np.array_equal(vm.flagcp, a["flagcp"])
+    assert vm.meta["cp_offset_int_u"] == sc.offset[0] and vm.meta["name_i0"].endswith("_i0.tif")
     assert a["vx"].shape == (sc.dimy, sc.dimx)
     for k in ("vx", "vy", "ex", "ey", "qual"):
         assert np.array_equal(np.isnan(a[k]), np.isnan(b[k])), k
