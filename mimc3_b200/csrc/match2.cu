@@ -98,14 +98,22 @@ struct Sums {
 // registers, 3 CTAs), ocw 30 keeps 31 in half-CTA groups; measured on B200 (profiles/).
 // ocw 30 runs two 128-thread groups (two nodes) per CTA, 3 CTAs = 6 nodes per SM; its 256-thread
 // instantiation only serves the wide-search-area bins (<= 2 CTAs per SM).
-constexpr int min_ctas(int ocw, int G) { return G == 256 && ocw < 30 ? 6 : (ocw == 15 ? 2 : (ocw == 30 ? 3 : 4)); }
+// ocw 40: one 256-thread CTA per node, four per SM at 64 registers; its wider-search-area bins run 128-thread CTAs
+// (two chip rows per thread, three per SM) or 256-thread CTAs compiled for two per SM (no register pressure).
+// The 256-thread instantiations of ocw 7/15 only serve bins with <= 3 CTAs per SM.
+constexpr int min_ctas(int ocw, int G) { return G == 256 && ocw < 30 ? 3 : (ocw == 15 ? 2 : (ocw == 30 ? 3 : (G == 128 ? 3 : 4))); }
 
 template <int OCW, int G>
 struct Cfg {
     static constexpr int S = 2 * OCW + 1;
-    static constexpr int NSEG = (G / S) < S ? (G / S) : S;   // row segments per chip row (at most one pixel each)
+    // A thread keeps RB chip rows (r, r + RPT, ...) of one column segment: RB = 2 lets half as many threads
+    // hold the 81x81 chip (54 pixels each), which is what fits five nodes into an SM's register file.
+    static constexpr int RB = (OCW == 40 && G == 128) ? 2 : 1;
+    static constexpr int RPT = (S + RB - 1) / RB;            // rows per row block
+    static constexpr int NSEG = (G / RPT) < S ? (G / RPT) : S;   // row segments per chip row (at most one pixel each)
     static constexpr int L = (S + NSEG - 1) / NSEG;
-    static constexpr int NGROUPS = kThreads / G;
+    static constexpr int NGROUPS = RB == 2 ? 1 : kThreads / G;   // groups (nodes) per CTA
+    static constexpr int CTA = G * NGROUPS;
     static constexpr int NWARPS = G / 32;
     // cells per evaluation round: 64 lets the ~39 first-probe cells of a static node go in one round
     // (worth it for the biggest chip, where a round is long); 32 keeps the control block small
@@ -257,7 +265,7 @@ struct Ctl {
 // the tile pointer and the pitch in registers.
 template <int OCW, int G, bool EXACTP, typename CtlT>
 __device__ __forceinline__ void node_rounds(const Match2Args &a, CtlT &ctl, float *sa, const float *sa_thread,
-                                            const float (&chip)[Cfg<OCW, G>::L], const int pitch, const bool active, const int t,
+                                            const float (&chip)[Cfg<OCW, G>::RB][Cfg<OCW, G>::L], const int pitch, const int row2, const bool active, const int t,
                                             const int lane, const int gwarp) {
     using C = Cfg<OCW, G>;
     constexpr int S = C::S, L = C::L;
@@ -456,16 +464,20 @@ __device__ __forceinline__ void node_rounds(const Match2Args &a, CtlT &ctl, floa
                     const int cy = job_cy(job), cx = job_cx(job);
                     unsigned int hi = 0;
                     int lo = 0;
-                    {   // threads without chip pixels (r = col0 = 0, chip all zero) run the same code: no branch
-                        const float *sp = sa_thread + (cy + 1) * pitch + (cx + 1);
+#pragma unroll
+                    for (int rb = 0; rb < C::RB; rb++) {
+                        // threads without chip pixels (r = col0 = 0, chip all zero) run the same code: no branch; a
+                        // thread whose second row does not exist reads its first row again (times zero)
+                        const float *sp = sa_thread + (cy + 1) * pitch + (cx + 1) + (rb ? row2 : 0);
                         // Two pixels per instruction (FMUL2 / FADD2 / FFMA2, sm_100): lane 0 of the packed pair
                         // accumulates the even pixels, lane 1 the odd ones -- the same two accumulators as a
-                        // scalar loop would keep, at half the issue slots.
+                        // scalar loop would keep, at half the issue slots.  One accumulator pair per chip row
+                        // (<= 16 pixels per accumulator).
                         f32x2 acc = pack2(a.A0, a.A0), lo2 = pack2(a.Mlo, a.Mlo);
 #pragma unroll
                         for (int k = 0; k < L; k += 2) {
                             // an odd L ends with a (pixel, 0) pair: the zero is a literal, not a load
-                            const f32x2 rv = pack2(chip[k], k + 1 < L ? chip[k + 1] : 0.0f);
+                            const f32x2 rv = pack2(chip[rb][k], k + 1 < L ? chip[rb][k + 1] : 0.0f);
                             const f32x2 sv = pack2(sp[k], k + 1 < L ? sp[k + 1] : 0.0f);
                             if (EXACTP) {
                                 // every product is exact in FP32 (scaled operands < 2^12): fma(r, s, acc) ==
@@ -485,8 +497,8 @@ __device__ __forceinline__ void node_rounds(const Match2Args &a, CtlT &ctl, floa
                         float acc0, acc1, lo0, lo1;
                         unpack2(acc, acc0, acc1);
                         unpack2(lo2, lo0, lo1);
-                        hi = (__float_as_uint(acc0) - a.A0_bits) + (__float_as_uint(acc1) - a.A0_bits);
-                        lo = (int)(__float_as_uint(lo0) - a.Mlo_bits) + (int)(__float_as_uint(lo1) - a.Mlo_bits);
+                        hi += (__float_as_uint(acc0) - a.A0_bits) + (__float_as_uint(acc1) - a.A0_bits);
+                        lo += (int)(__float_as_uint(lo0) - a.Mlo_bits) + (int)(__float_as_uint(lo1) - a.Mlo_bits);
                     }
                     hi = __reduce_add_sync(0xffffffffu, hi);
                     lo = __reduce_add_sync(0xffffffffu, lo);
@@ -554,11 +566,13 @@ __device__ __forceinline__ void node_rounds(const Match2Args &a, CtlT &ctl, floa
                     const int cy = job_cy(job), cx = job_cx(job);
                     const int cell = cy * ctl.geo.cw + cx;
                     Sums s = {0.0, 0.0, 0.0, 0.0, 0.0, 0};
-                    if (active) {
-                        const float *sp = sa_thread + (cy + 1) * pitch + (cx + 1);
+#pragma unroll
+                    for (int rb = 0; rb < C::RB; rb++) {
+                        if (!active) break;
+                        const float *sp = sa_thread + (cy + 1) * pitch + (cx + 1) + (rb ? row2 : 0);
 #pragma unroll
                         for (int k = 0; k < L; k++) {
-                            const float rv = chip[k], sv = sp[k];
+                            const float rv = chip[rb][k], sv = sp[k];
                             if (rv >= a.min_dn && sv >= a.min_dn) {   // null exclusion, :723
                                 s.n++;
                                 s.sx += (double)rv; s.sy += (double)sv;
@@ -621,8 +635,8 @@ __device__ __forceinline__ void node_rounds(const Match2Args &a, CtlT &ctl, floa
     }
 }
 
-template <int OCW, int G, bool EXACTP>
-__global__ void __launch_bounds__(kThreads, min_ctas(OCW, G)) match2_kernel(const Match2Args a) {
+template <int OCW, int G, bool EXACTP, int MINCTA = min_ctas(OCW, G)>
+__global__ void __launch_bounds__(Cfg<OCW, G>::CTA, MINCTA) match2_kernel(const Match2Args a) {
     using C = Cfg<OCW, G>;
     constexpr int S = C::S, L = C::L;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -637,7 +651,7 @@ __global__ void __launch_bounds__(kThreads, min_ctas(OCW, G)) match2_kernel(cons
     float *sa = (float *)(smem_raw + (size_t)grp * a.grp_bytes);
 
     // this thread's chip slice: row r, columns [col0, col0+len)
-    const int seg = t / S, r = t - seg * S;
+    const int seg = t / C::RPT, r = t - seg * C::RPT;   // rows r, r + RPT, ... of column segment seg
     const bool active = seg < C::NSEG;
     const int col0 = seg * L;
     const int len = active ? min(L, S - col0) : 0;
@@ -731,9 +745,11 @@ __global__ void __launch_bounds__(kThreads, min_ctas(OCW, G)) match2_kernel(cons
             }
             continue;
         }
-        float chip[L];
+        float chip[C::RB][L];
 #pragma unroll
-        for (int c = 0; c < L; c++) chip[c] = (c < len) ? sa[r * S + col0 + c] : 0.0f;
+        for (int rb = 0; rb < C::RB; rb++)
+#pragma unroll
+            for (int c = 0; c < L; c++) chip[rb][c] = (c < len && r + rb * C::RPT < S) ? sa[(r + rb * C::RPT) * S + col0 + c] : 0.0f;
         gsync<G>();
 
         // ---- stage the search area (extract_sarea :857-890): zero outside the image, zero in the
@@ -763,7 +779,8 @@ __global__ void __launch_bounds__(kThreads, min_ctas(OCW, G)) match2_kernel(cons
         PROF_T(t_stage1);
         PROF_ADD(1, t_stage1 - t_node0);
         // this thread's view of the tile: row r, first column col0 (threads without chip pixels: the origin)
-        node_rounds<OCW, G, EXACTP>(a, ctl, sa, sa + (active ? r * pitch + col0 : 0), chip, pitch, active, t, lane, gwarp);
+        node_rounds<OCW, G, EXACTP>(a, ctl, sa, sa + (active ? r * pitch + col0 : 0), chip, pitch,
+                                    (C::RB > 1 && active && r + C::RPT < S) ? C::RPT * pitch : 0, active, t, lane, gwarp);
         PROF_T(t_node1);
         PROF_ADD(0, t_node1 - t_node0);
         PROF_ADD(6, 1);
@@ -776,9 +793,9 @@ float min_dn_float() {
     return f;
 }
 
-template <int OCW, int G, bool EXACTP>
+template <int OCW, int G, bool EXACTP, int MINCTA = min_ctas(OCW, G)>
 int launch_one(mimc3cu_ctx *ctx, Match2Args &a, int groups_per_cta, size_t smem, int n_list, long long *grid_out) {
-    auto kern = match2_kernel<OCW, G, EXACTP>;
+    auto kern = match2_kernel<OCW, G, EXACTP, MINCTA>;
     const int threads = G * groups_per_cta;   // <= kThreads; the kernel only needs whole groups
     CU_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -806,7 +823,7 @@ inline int bin_table(int ocw, BinCfg *t) {
     // ocw 30: half a CTA per node (chip rows in two 31-pixel segments), 6 or 4 nodes per SM at <= 85 registers
     // (measured: 8 nodes per SM at 64 registers spill and lose 20 %), then whole CTAs for the wide search areas
     if (ocw == 30) { t[0] = {128, 2, 3}; t[1] = {128, 2, 2}; t[2] = {256, 1, 2}; t[3] = {256, 1, 1}; return 4; }
-    if (ocw >= 30) { t[0] = {256, 1, 4}; t[1] = {256, 1, 3}; t[2] = {256, 1, 2}; t[3] = {256, 1, 1}; return 4; }
+    if (ocw >= 30) { t[0] = {256, 1, 4}; t[1] = {128, 1, 3}; t[2] = {256, 1, 2}; t[3] = {256, 1, 1}; return 4; }
     // small chips: a warp per node while eight nodes (one CTA) fit on an SM; nodes with very wide search
     // areas (fast ice) would leave the SM with one or two warps that way, so they get a whole
     // 256-thread CTA each (row segments of <= 4 pixels per thread): more instructions per cell, but
@@ -835,7 +852,7 @@ static size_t static_smem_bytes(int ocw, int G) {
         case 7: e = G == 256 ? cudaFuncGetAttributes(&fa, match2_kernel<7, 256, false>) : cudaFuncGetAttributes(&fa, match2_kernel<7, 32, false>); break;
         case 15: e = G == 256 ? cudaFuncGetAttributes(&fa, match2_kernel<15, 256, false>) : cudaFuncGetAttributes(&fa, match2_kernel<15, 32, false>); break;
         case 30: e = G == 256 ? cudaFuncGetAttributes(&fa, match2_kernel<30, 256, false>) : cudaFuncGetAttributes(&fa, match2_kernel<30, 128, false>); break;
-        case 40: e = cudaFuncGetAttributes(&fa, match2_kernel<40, 256, false>); break;
+        case 40: e = G == 256 ? cudaFuncGetAttributes(&fa, match2_kernel<40, 256, false>) : cudaFuncGetAttributes(&fa, match2_kernel<40, 128, false>); break;
     }
     return e == cudaSuccess ? fa.sharedSizeBytes : 12288;
 }
@@ -954,8 +971,11 @@ int launch_match2(mimc3cu_ctx *ctx, const MatchLaunch &L, const Image *ref, cons
                 if (tab[k].G == 256) rc = exactp ? launch_one<30, 256, true>(ctx, a, 1, smem, a.n_list, nullptr) : launch_one<30, 256, false>(ctx, a, 1, smem, a.n_list, nullptr);
                 else rc = exactp ? launch_one<30, 128, true>(ctx, a, tab[k].groups, smem, a.n_list, nullptr) : launch_one<30, 128, false>(ctx, a, tab[k].groups, smem, a.n_list, nullptr);
                 break;
-            case 40: rc = exactp ? launch_one<40, 256, true>(ctx, a, tab[k].groups, smem, a.n_list, nullptr)
-                                : launch_one<40, 256, false>(ctx, a, tab[k].groups, smem, a.n_list, nullptr); break;
+            case 40:
+                if (tab[k].G == 128) rc = exactp ? launch_one<40, 128, true>(ctx, a, 1, smem, a.n_list, nullptr) : launch_one<40, 128, false>(ctx, a, 1, smem, a.n_list, nullptr);
+                else if (tab[k].ctas <= 2) rc = exactp ? launch_one<40, 256, true, 2>(ctx, a, 1, smem, a.n_list, nullptr) : launch_one<40, 256, false, 2>(ctx, a, 1, smem, a.n_list, nullptr);
+                else rc = exactp ? launch_one<40, 256, true>(ctx, a, 1, smem, a.n_list, nullptr) : launch_one<40, 256, false>(ctx, a, 1, smem, a.n_list, nullptr);
+                break;
             default: return mimc3cu_fail(ctx, "match2: unsupported ocw %d", L.ocw);
         }
         if (rc) return rc;
