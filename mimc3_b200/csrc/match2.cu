@@ -115,9 +115,9 @@ struct Cfg {
     static constexpr int NGROUPS = RB == 2 ? 1 : kThreads / G;   // groups (nodes) per CTA
     static constexpr int CTA = G * NGROUPS;
     static constexpr int NWARPS = G / 32;
-    // cells per evaluation round: 64 lets the ~39 first-probe cells of a static node go in one round
-    // (worth it for the biggest chip, where a round is long); 32 keeps the control block small
-    static constexpr int MAXJ = OCW == 40 ? 64 : 32;
+    // cells per evaluation round: one slot per lane of the finalizing warp.  (64, so that the ~39 first-probe cells
+    // of a static node go in one round, costs ten more live registers in the compute loop: 5 % slower at ocw 40.)
+    static constexpr int MAXJ = 32;
     static constexpr int NH = MAXJ / 32;
     static_assert(NSEG >= 1, "group too small for this chip");
     static_assert((L + 1) / 2 <= 16, "at most 16 pixels per FP32 accumulator");
