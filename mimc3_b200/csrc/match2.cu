@@ -15,26 +15,30 @@
 //    FP32 with an error-free transformation (Fast2Sum against a running accumulator biased by a
 //    power of two A0 >= 16 * max product):
 //        p = r*s;  t = acc + p;  z = t - acc;  e = p - z;  acc = t;  lo += e
-//    i.e. 1 FMUL + 4 FADD per pixel on the FP32 pipes, no conversion.  acc stays in one binade
-//    [A0, 2*A0], so float_as_uint(acc) - float_as_uint(A0) is the partial sum in units of
-//    ulp(A0); lo is biased by 1.5*2^23 units the same way.  Both are then reduced as integers
-//    (REDUX.SUM), and the cell is normalised in FP64 with the reference's expression (:734).
-//    Pairs whose products are all exact in FP32 (u8 and filtered-u8 data) use the FFMA form of the
-//    same transformation, one instruction less per pixel.
+//    i.e. 1 FMUL + 4 FADD per pixel on the FP32 pipes, no conversion -- issued as packed pairs
+//    (FFMA2 / FADD2, two pixels per instruction; the even/odd accumulators are the two lanes).
+//    acc stays in one binade [A0, 2*A0], so float_as_uint(acc) - float_as_uint(A0) is the partial
+//    sum in units of ulp(A0); lo is biased by 1.5*2^23 units the same way.  Both are then reduced
+//    as integers (REDUX.SUM), and the cell is normalised in FP64 with the reference's expression
+//    (:734).  Pairs whose products are all exact in FP32 (u8 and filtered-u8 data) use the FFMA
+//    form of the same transformation, one instruction less per pixel.
 //  * The never-written last row/column of the search area only drops the chip's
 //    last row/column from the joint mask: those cells stay on the fast path with trimmed SAT
 //    rectangles.  Cells that touch a real null pixel or the zero-filled image border are
 //    re-evaluated with the masked 5-sum FP64 loop in a separate round.
 //
-// Work decomposition: a "group" of G threads owns one node at a time (G = 256, one CTA, for chip
-// half-widths 30/40 and for very wide search areas; G = 32, one warp, otherwise for 7/15).  Thread
-// (k, r) keeps the L pixels of chip row r, segment k in REGISTERS; the search area is staged in
-// shared memory (loads issued eight deep) with an odd pitch so that the row-per-lane access
-// pattern is bank-conflict free.  The reference's hill-climbing state machine (pivot order,
-// first-wins ties, "newly evaluated" stop rule, -2.0 placeholders) runs verbatim in warp 0 of the
-// group, its state kept in the shared control block; the first 3x3 probe of every pivot is
-// unconditional and is evaluated up-front in rounds of <= 32 (64 for the 81x81 chip) cells.
-// Launches are split into shared-memory bins by the nodes' pivot extent (bin_table); nodes that
+// Work decomposition: a "group" of G threads owns one node at a time: one warp for chip
+// half-widths 7/15 (eight nodes per CTA), half a CTA for 30, a whole 256-thread CTA for 40 and
+// for wide search areas, a 128-thread CTA holding two chip rows per thread for the middle bin of
+// 40 (Cfg, bin_table).  Thread (k, r) keeps the L pixels of chip row r, segment k in REGISTERS;
+// the search area is staged in shared memory (loads issued eight deep) with an odd pitch so that
+// the row-per-lane access pattern is bank-conflict free.  The reference's hill-climbing state
+// machine (pivot order, first-wins ties, "newly evaluated" stop rule, -2.0 placeholders) runs
+// verbatim in warp 0 of the group, its state kept in the shared control block; the first 3x3
+// probe of every pivot is unconditional and is evaluated up-front in rounds of <= 32 cells, then
+// the second probes of all pivots are predicted lane-parallel and evaluated in one round.
+// Launches are split into shared-memory bins by the nodes' pivot extent (bin_table), each bin
+// with the instantiation compiled for its number of resident CTAs (register budget); nodes that
 // fit no bin go to the general kernel within the same call.
 #include <math_constants.h>
 
