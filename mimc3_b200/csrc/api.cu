@@ -433,10 +433,10 @@ int mimc3cu_match_async(mimc3cu_ctx *ctx, int32_t ref_img, int32_t search_img, c
         ScopedTimer tm(ctx, 0);
         rc = v2 ? launch_match2(ctx, L, r, s, &ps) : launch_match(ctx, L);
     }
-    if (!rc) {
-        if (!ps.last_use) CU_CHECK(ctx, cudaEventCreateWithFlags(&ps.last_use, cudaEventDisableTiming));
-        CU_CHECK(ctx, cudaEventRecord(ps.last_use, ctx->stream));
-    }
+    // recorded even after a failed launch sequence: some of its kernels may already be reading the slot
+    if (!ps.last_use && cudaEventCreateWithFlags(&ps.last_use, cudaEventDisableTiming) != cudaSuccess) ps.last_use = nullptr;
+    if (ps.last_use) cudaEventRecord(ps.last_use, ctx->stream);
+    else if (!rc) CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));   // no event: fall back to a full wait
     return rc;
 }
 
