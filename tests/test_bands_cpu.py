@@ -143,3 +143,22 @@ def test_halo_exchange_over_threads():
     for t in th:
         t.join(timeout=60)
     assert all(o == [] for o in out), out
+
+
+def test_split_rows_property():
+    """Bands are contiguous, cover every row once and respect the minimum height for any weights."""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+
+    @hyp.settings(max_examples=100, deadline=None)
+    @hyp.given(st.integers(1, 8), st.integers(1, 6), st.integers(0, 40), st.integers(0, 2**31 - 1), st.booleans())
+    def check(world, min_rows, extra, seed, weighted):
+        dimy = world * min_rows + extra
+        w = np.random.default_rng(seed).random(dimy) ** 4 * 100 if weighted else None
+        parts = bands.split_rows(dimy, world, min_rows=min_rows, weights=w)
+        assert len(parts) == world and parts[0][0] == 0
+        assert all(n >= min_rows for _, n in parts)
+        assert all(parts[k][0] + parts[k][1] == parts[k + 1][0] for k in range(world - 1))
+        assert parts[-1][0] + parts[-1][1] == dimy
+
+    check()

@@ -96,3 +96,19 @@ def test_dp_dump_layout_and_reload(tmp_path):
     gma.write(tmp_path / "FT_result" / "dp_05.gma", np.zeros((10, 3), np.float32))
     with pytest.raises(ValueError):
         gma.load_dp(str(tmp_path))
+
+
+def test_gma_roundtrip_property():
+    """Any 2-D shape (including empty ones) and any byte pattern survive write -> read unchanged."""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+
+    @hyp.settings(max_examples=60, deadline=None)
+    @hyp.given(st.integers(0, 9), st.integers(0, 9), st.sampled_from(["float32", "float64", "int32", "uint8"]), st.integers(0, 2**31 - 1))
+    def check(nr, nc, dt, seed):
+        raw = np.random.default_rng(seed).integers(0, 256, size=nr * nc * np.dtype(dt).itemsize, dtype=np.uint8)
+        a = raw.view(dt).reshape(nr, nc)
+        b = gma.read(gma.dumps(a), dt)
+        assert b.shape == (nr, nc) and a.tobytes() == b.tobytes()      # NaN payloads included
+
+    check()
