@@ -62,6 +62,13 @@ WORKLOADS = {
     "c4": dict(H=8192, W=8192, dtype="u16", spacing=20, mpp=15.0, peak_px=43.0, apriori_gain=0.9, decorrelated_patches=200,
                band_width_frac=0.2, desc="fast-glacier case: ~43 px a-priori displacement, wide DLC windows, 8192x8192 u16"),
 }
+# configs[4] as ONE scene sharded over the GPUs (strong scaling): every rank holds both images and a contiguous band of
+# node rows; decorrelated patches make the iterative stages of the postprocess sweep (halo exchanges every sweep)
+WORKLOADS["c5s"] = dict(H=32768, W=32768, dtype="u8", spacing=8, mpp=15.0, peak_px=6.3, decorrelated_patches=3000, strong=True,
+                        desc="ONE 32768x32768 u8 synthetic mosaic, 8-px node spacing, node-row bands sharded over the GPUs, decorrelated patches")
+# the same layout at a size the CPU-side checks and 2-GPU development runs finish quickly
+WORKLOADS["c5s_small"] = dict(H=8192, W=8192, dtype="u8", spacing=8, mpp=15.0, peak_px=6.3, decorrelated_patches=200, strong=True,
+                              desc="ONE 8192x8192 u8 synthetic pair, 8-px node spacing, node-row bands sharded over the GPUs, decorrelated patches")
 VEC_OCW = (7, 15, 30, 40)
 
 
@@ -133,22 +140,38 @@ class ClockSampler:
 # -------------------------------------------------------------------------------------------
 # the reference / CPU arm
 # -------------------------------------------------------------------------------------------
-def cpu_reference_sample(i0, i1, filtered, xyuvav, dimx, dimy, dt, offset, target_nodes):
-    """Times the unmodified reference on a bounded sample: all 32 matching attempts on every
-    k-th node row (full-size images), plus conv2 on a row band scaled to the full image.
-    `filtered` = list of three (i0c, i1c) host pairs (bit-identical to the reference's conv2,
-    asserted by tests/test_conv2_gpu.py).  Returns dict with nodes/s for the whole workload."""
+def _host_threads():
+    """Host threads the CPU arm may use: all cores this process is allowed on (torchrun exports
+    OMP_NUM_THREADS=1 to its workers; the reference arm runs on rank 0 alone, so it takes them all)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_reference_sample(i0, i1, xyuvav, dimx, dimy, dt, offset, target_nodes, keep_dp=False, with_cp=True):
+    """Times the unmodified reference (oracle/_ref/libmimc3ref.so: MIMC_module.c + GMA.c compiled as they are) on a
+    bounded sample of the workload, with all host threads:
+      * all 32 matching attempts (MIMC_main.c:261-350) on every k-th node row of the full-size images, scaled
+        linearly in nodes;
+      * the six GMA_float_conv2 calls on the FULL images (the reference's own conv2, timed, not estimated);
+      * get_offset_image (the control-point stage) once, on the full node list.
+    Nothing of mimc3_b200's library is loaded or called here.  Returns a dict; with keep_dp also the
+    reference's dp (32, sample, 3) and the sampled node indices, for the parity verdict of the bench line."""
     import oracle
     H, W = i0.shape
     kind = "reference"
+    nthreads = _host_threads()
     try:
         R = oracle.Reference()
-        ncores = R.num_threads()
+        ncores = R.set_num_threads(nthreads)
         R.set_globals(xyuvav, dimx, dimy, dt)
-        mpp = float(np.float32((xyuvav[1, 0] - xyuvav[0, 0]) / (xyuvav[1, 2] - xyuvav[0, 2])))
-        match = lambda a, b, x, offs, off, piv, sign, ocw: R.match(a, b, x, offs, off, piv, sign, ocw)[1]
+        match = lambda a, b, x, offs, off, piv, sign, ocw: R.match(a, b, x, offs, off, piv, sign, ocw)
         pivots = lambda x, ocw: R.get_uv_pivot(x, dt, ocw, H, W)
         conv2 = R.conv2
+
+        def cp_stage():
+            t = time.perf_counter(); rc, off, _ = R.get_offset_image(i0, i1, xyuvav, fake_time=1); return time.perf_counter() - t, rc, off
     except (FileNotFoundError, OSError) as e:
         log(f"[bench] reference build not available ({e}); timing the oracle port instead")
         kind = "port"
@@ -157,36 +180,103 @@ def cpu_reference_sample(i0, i1, filtered, xyuvav, dimx, dimy, dt, offset, targe
         mpp = float(np.float32((xyuvav[1, 0] - xyuvav[0, 0]) / (xyuvav[1, 2] - xyuvav[0, 2])))
 
         def match(a, b, x, offs, off, piv, sign, ocw):
-            t = time.perf_counter(); O.match(a, b, x, offs, off, piv, sign, ocw); return time.perf_counter() - t
+            t = time.perf_counter(); out = O.match(a, b, x, offs, off, piv, sign, ocw)[0]; return out, time.perf_counter() - t
         pivots = lambda x, ocw: O.get_uv_pivot(x, dt, mpp, ocw, H, W)
         conv2 = O.conv2
+
+        def cp_stage():
+            t = time.perf_counter(); rc, off, _ = O.get_offset_image(i0, i1, xyuvav, 1); return time.perf_counter() - t, rc, off
     n = dimx * dimy
     rows = max(1, min(dimy, int(round(target_nodes / dimx))))
     step = max(1, dimy // rows)
     sel_rows = np.arange(step // 2, dimy, step)[:rows]
     idx = (sel_rows[:, None] * dimx + np.arange(dimx)[None, :]).ravel()
     xs = np.ascontiguousarray(xyuvav[idx])
-    t_match = 0.0
-    pairs = [(i0, i1)] + list(filtered)
-    for (a, b) in pairs:
-        for ocw in VEC_OCW:
-            off, piv = pivots(xs, ocw)
-            t_match += match(a, b, xs, offset, off, piv, +1, ocw)
-            t_match += match(b, a, xs, -offset, off, piv, -1, ocw)
-    # conv2: 6 calls on a band of rows, scaled by the pixel ratio (the loop is O(H*W), single-threaded)
-    band = min(H, 1024)
-    src = np.ascontiguousarray(i0[:band]); dst = np.zeros_like(src)
-    t0 = time.perf_counter()
-    for k in range(3):
-        conv2(src, k, dst)
-    t_conv_band = (time.perf_counter() - t0) * 2.0   # two images
-    t_conv_full = t_conv_band * (H / band)
-    t_total = t_match * (n / len(idx)) + t_conv_full
-    return {"value": n / t_total, "unit": "nodes/s", "cores": int(ncores), "kind": kind,
-            "sample": f"all 32 attempts on {len(idx)} of {n} nodes ({len(sel_rows)} evenly spaced node rows, full-size images; "
-                      f"{t_match:.2f} s, scaled linearly in nodes) + 6 conv2 calls on a {band}-row band scaled by H/{band} "
-                      f"({t_conv_full:.2f} s est.); postprocess (<0.3 % of CPU time) not included",
-            "t_match_sample_s": t_match, "t_conv2_full_est_s": t_conv_full, "sample_nodes": int(len(idx))}
+    piv = [pivots(xs, ocw) for ocw in VEC_OCW]
+    dp = np.zeros((32, len(idx), 3), np.float32) if keep_dp else None
+    t_match = t_conv = 0.0
+    # main allocates i0c / i1c once (zero-initialised under the oracle's allocator shim) and reuses them for the
+    # three filters (MIMC_main.c:304-349): the same here, so the stale-border semantics of conv2 are the reference's
+    c0 = np.zeros_like(i0); c1 = np.zeros_like(i1)
+    for variant in range(4):
+        a, b = i0, i1
+        if variant > 0:
+            t0 = time.perf_counter()
+            conv2(i0, variant - 1, c0); conv2(i1, variant - 1, c1)
+            t_conv += time.perf_counter() - t0
+            a, b = c0, c1
+        for c, ocw in enumerate(VEC_OCW):
+            off, pv = piv[c]
+            k = variant * 8 + c * 2
+            d0, s0 = match(a, b, xs, offset, off, pv, +1, ocw)
+            d1, s1 = match(b, a, xs, -offset, off, pv, -1, ocw)
+            t_match += s0 + s1
+            if keep_dp:
+                dp[k] = d0
+                dp[k + 1] = d1 * np.array([-1, -1, 1], np.float32)    # main negates du, dv of the swapped pass (:289-293)
+    del c0, c1
+    t_cp, cp_rc, cp_off = (0.0, 0, None)
+    if with_cp:
+        t_cp, cp_rc, cp_off = cp_stage()
+    t_total = t_match * (n / len(idx)) + t_conv + t_cp
+    res = {"value": n / t_total, "unit": "nodes/s", "cores": int(ncores), "kind": kind,
+           "sample": f"all 32 attempts on {len(idx)} of {n} nodes ({len(sel_rows)} evenly spaced node rows, full-size images; "
+                     f"{t_match:.2f} s, scaled linearly in nodes) + the 6 conv2 calls on the full images ({t_conv:.2f} s) + "
+                     f"get_offset_image once ({t_cp:.2f} s); postprocess (<0.3 % of CPU time) not included; {ncores} OpenMP threads",
+           "t_match_sample_s": t_match, "t_conv2_s": t_conv, "cp_stage_ms": 1e3 * t_cp, "cp_offset": None if cp_off is None else [int(cp_off[0]), int(cp_off[1])],
+           "sample_nodes": int(len(idx))}
+    if keep_dp:
+        res["dp"] = dp; res["idx"] = idx
+    return res
+
+
+def parity_verdict(ref, dp_gpu, peak_gpu, ncell_gpu, i0, i1, xyuvav, dimx, dimy, dt, offset, ctx, params_for):
+    """Per-config parity verdict for the bench line: the GPU results of the measured
+    workload against the unmodified reference on the sampled nodes (dp of all 32 attempts, bit for bit), against the
+    oracle for what the reference keeps internal (integer peaks, evaluated-cell counts; raw-pair attempts), and the
+    postprocess of a band of node rows against the oracle's (cluster choice per node)."""
+    import oracle
+    idx = ref["idx"]
+    a = ref["dp"]; b = dp_gpu[:, idx, :]
+    na, nb = np.isnan(a), np.isnan(b)
+    bad = (na != nb) | (~na & ~nb & (a.view(np.uint32) != b.view(np.uint32)))
+    flags_a = np.where(a[..., 2] <= -2.0, a[..., 2], 0.0); flags_b = np.where(b[..., 2] <= -2.0, b[..., 2], 0.0)
+    fin = ~na[..., 0] & ~nb[..., 0] & ~na[..., 1] & ~nb[..., 1]
+    dsub = float(np.max(np.abs(a[..., :2][fin] - b[..., :2][fin]), initial=0.0))
+    okn = np.isfinite(a[..., 2]) & np.isfinite(b[..., 2]) & (a[..., 2] > -2.0)
+    drel = float(np.max(np.abs(a[..., 2][okn] - b[..., 2][okn]) / np.maximum(np.abs(a[..., 2][okn]), 1e-30), initial=0.0))
+    out = {"reference_nodes": int(len(idx)), "attempts": 32, "dp_values_compared": int(a.size),
+           "dp_mismatches": int(bad.sum()), "flag_mismatches": int((flags_a != flags_b).sum()),
+           "max_abs_subpixel_diff_px": dsub, "max_rel_ncc_diff": drel}
+    # integer peaks / evaluated cells: the oracle on the same sampled nodes, the eight raw-pair attempts
+    O = oracle.Oracle()
+    H, W = i0.shape
+    mpp = float(np.float32((xyuvav[1, 0] - xyuvav[0, 0]) / (xyuvav[1, 2] - xyuvav[0, 2])))
+    xs = np.ascontiguousarray(xyuvav[idx])
+    pm = nm = 0
+    for c, ocw in enumerate(VEC_OCW):
+        off, pv = O.get_uv_pivot(xs, dt, mpp, ocw, H, W)
+        for d, (x, y, o, sg) in enumerate(((i0, i1, offset, +1), (i1, i0, -offset, -1))):
+            _, pk, nc = O.match(x, y, xs, o, off, pv, sg, ocw)
+            k = c * 2 + d
+            pm += int((pk != peak_gpu[k][idx]).any(axis=1).sum()); nm += int((nc != ncell_gpu[k][idx]).sum())
+    out.update(peak_nodes=int(len(idx)), peak_attempts=8, peak_mismatches=pm, ncell_mismatches=nm)
+    # cluster choice: postprocess of a contiguous band of node rows taken as a grid of its own, GPU vs oracle
+    rows = min(dimy, 24)
+    r0 = (dimy - rows) // 2
+    band = np.arange(r0 * dimx, (r0 + rows) * dimx)
+    xb = np.ascontiguousarray(xyuvav[band]); dpb = np.ascontiguousarray(dp_gpu[:, band, :])
+    pp = oracle.post_params(xb, dimx, rows, dt)
+    st = O.postprocess_stages(dpb, xb, pp)
+    import torch
+    pb = params_for(xb, dimx, rows, dt)
+    dpd = torch.from_numpy(dpb).cuda(); planes = torch.empty((5, rows, dimx), dtype=torch.float32, device="cuda")
+    gstats = ctx.postprocess(dpd, xb, pb, planes)
+    gid = ctx.postprocess_stage(4, rows * dimx)
+    out.update(cluster_nodes=int(rows * dimx), cluster_mismatches=int((gid != st["ps_id"]).sum()),
+               cluster_band_sweeps={"dpf1": int(gstats[0]), "pseudosmoothing": int(gstats[1]),
+                                    "oracle_dpf1": int(st["dpf1_sweeps"]), "oracle_pseudosmoothing": int(st["ps_sweeps"])})
+    return out
 
 
 def main():
@@ -199,6 +289,8 @@ def main():
     ap.add_argument("--cpu-sample-nodes", type=int, default=0, help="nodes in the CPU baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--band-comm", default="nccl", choices=["nccl", "python"],
+                    help="N > 1: halo exchange inside the library (NCCL, default) or through the Python callbacks of bands.py")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         log("[bench] note: timing rules ask for >= 3 warm-up steps")
@@ -225,6 +317,7 @@ def main():
 
     wl = dict(WORKLOADS[args.workload])
     desc = wl.pop("desc")
+    strong = bool(wl.pop("strong", False))
     have_gpu = torch.cuda.is_available()
     if args.impl == "ours" and not have_gpu:
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
@@ -239,7 +332,7 @@ def main():
         dist.init_process_group(backend="nccl", device_id=dev)
 
     t_gen = time.perf_counter()
-    sc = synth.make_scene(seed=1234 + rank, device=dev, **wl)
+    sc = synth.make_scene(seed=1234 + (0 if strong else rank), device=dev, **wl)
     H, W = sc.shape
     n = sc.n
     offset = np.array(sc.offset, np.int32)
@@ -247,98 +340,132 @@ def main():
     config = {"workload": f"{args.workload}: {desc}", "image": [H, W], "image_dtype": sc.dtype, "nodes_per_gpu": n,
               "node_grid_per_gpu": [sc.dimy, sc.dimx], "attempts_per_node": 32, "chip_half_widths": list(VEC_OCW),
               "l2_policy": "inputs larger than L2 (4 float32 images of %.2f GB each are streamed every step)" % (H * W * 4 / 1e9),
-              "parallelism": f"node-row bands x{world}" if world > 1 else "single GPU"}
+              "parallelism": (f"node-row bands x{world} of one scene" if strong else f"node-row bands x{world} (one tile per GPU)") if world > 1 else "single GPU"}
 
     # ------------------------------------------------------------------------------- reference arm
     if args.impl == "reference":
+        # the reference's own CPU implementation only: nothing of libmimc3cu.so is loaded by this process
+        # (the filtered pairs come from the reference's GMA_float_conv2, timed as part of the unit)
         i0 = sc.i0.cpu().numpy(); i1 = sc.i1.cpu().numpy()
-        filtered = []
-        if have_gpu:
-            from mimc3_b200 import pipeline
-            import oracle
-            pl = pipeline.Pipeline(local_rank)
-            pl.set_images(sc.i0, sc.i1)
-            for k in range(3):
-                pl.ctx.conv2(pl.handles["i0"], oracle.KERNELS[k], pl.handles["i0c"])
-                pl.ctx.conv2(pl.handles["i1"], oracle.KERNELS[k], pl.handles["i1c"])
-                filtered.append((pl.ctx.image_download(pl.handles["i0c"], H, W), pl.ctx.image_download(pl.handles["i1c"], H, W)))
-            pl.close()
-        else:
-            import oracle
-            O = oracle.Oracle()
-            c0 = np.zeros_like(i0); c1 = np.zeros_like(i1)
-            for k in range(3):
-                O.conv2(i0, k, c0); O.conv2(i1, k, c1)
-                filtered.append((c0.copy(), c1.copy()))
         del sc.i0, sc.i1
         target = args.cpu_sample_nodes or 4 * sc.dimx
-        res = None
-        times = []
-        for it in range(args.warmup + args.steps):
-            t0 = time.perf_counter()
-            res = cpu_reference_sample(i0, i1, filtered, sc.xyuvav, sc.dimx, sc.dimy, sc.dt, offset, target)
-            if it >= args.warmup:
-                times.append((time.perf_counter() - t0, res["value"]))
-        value = float(np.mean([v for _, v in times]))
+        reps = max(1, min(args.steps, 2))        # a bounded sample, not `steps` repetitions of it
+        if args.warmup > 0:                       # warm the OpenMP pool on a handful of nodes
+            cpu_reference_sample(i0[:1024, :1024].copy(), i1[:1024, :1024].copy(), sc.xyuvav[:8], 8, 1, sc.dt, offset, 8, with_cp=False)
+        vals, res = [], None
+        for it in range(reps):
+            res = cpu_reference_sample(i0, i1, sc.xyuvav, sc.dimx, sc.dimy, sc.dt, offset, target)
+            vals.append(res["value"])
+        value = float(np.mean(vals))
         line = {"impl": "reference", "metric": "grid nodes matched per second", "value": value, "unit": "nodes/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * n / value, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 products, f64 accumulation", "data": "synthetic",
-                "config": config,
+                "config": config, "sample_repetitions": reps, "cp_stage_ms": res["cp_stage_ms"], "cp_offset": res["cp_offset"],
+                "conv2_s": res["t_conv2_s"],
                 "cpu_baseline": {"value": value, "unit": "nodes/s", "cores": res["cores"], "kind": res["kind"], "sample": res["sample"]},
                 "e2e": {"value": value, "unit": "nodes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit_json(line)
         return 0
 
     # ------------------------------------------------------------------------------- our arm
-    from mimc3_b200 import lib, pipeline
+    from mimc3_b200 import bands, lib, pipeline
     pl = pipeline.Pipeline(local_rank)
     ctx = pl.ctx
     pl.set_images(sc.i0, sc.i1)
-    pl.set_grid(sc.xyuvav, sc.dimx, sc.dimy, sc.dt)
+    # ---- the node grid and this rank's band of node rows -------------------------------------------------
+    #   N = 1   : the whole grid
+    #   weak    : the ranks' grids stacked along y are the bands of one mosaic grid (one tile per GPU)
+    #   strong  : one scene; contiguous bands balanced by the matching cost of their rows (sum of P + 2, known
+    #             before matching); every rank holds both images
+    dimx = sc.dimx
+    if world == 1:
+        gxy, gdimy, row0, rows = sc.xyuvav, sc.dimy, 0, sc.dimy
+        band_rows = [(0, sc.dimy)]
+    elif strong:
+        gxy, gdimy = sc.xyuvav, sc.dimy
+        p0 = lib.params_for(gxy, dimx, gdimy, sc.dt)
+        halo = lib.band_halo(p0)
+        work = bands.row_work([lib.get_uv_pivot(gxy, sc.dt, p0.mpp, ocw, H, W)[0] for ocw in VEC_OCW], dimx, gdimy)
+        band_rows = bands.split_rows(gdimy, world, min_rows=halo, weights=work)
+        row0, rows = band_rows[rank]
+    else:
+        xy_all = [None] * world
+        dist.all_gather_object(xy_all, sc.xyuvav)
+        gxy = np.concatenate(xy_all, axis=0)
+        for r in range(world):     # map-y continues down the mosaic so that the global grid is regular
+            gxy[r * sc.n:(r + 1) * sc.n, 1] -= r * sc.dimy * sc.spacing * sc.mpp
+        gdimy, row0, rows = sc.dimy * world, rank * sc.dimy, sc.dimy
+        band_rows = [(r * sc.dimy, sc.dimy) for r in range(world)]
+    n_total = dimx * gdimy if (strong or world == 1) else sc.n * world
+    n = rows * dimx                                     # this rank's nodes
+    # weak scaling: the rank's own tile is matched with its LOCAL node coordinates; the global grid only drives the postprocess
+    xy_band = np.ascontiguousarray(gxy[row0 * dimx:(row0 + rows) * dimx]) if (strong or world == 1) else sc.xyuvav
+    gparams = lib.params_for(gxy, dimx, gdimy, sc.dt)
+    pl.set_grid(xy_band, dimx, rows, sc.dt)
     params = pl.params
+    config["nodes_per_gpu"] = n if world == 1 or not strong else [r * dimx for _, r in band_rows]
+    config["nodes_total"] = n_total
+    config["node_grid"] = [gdimy, dimx]
     # host copies for the e2e leg (pinned) and the CPU baseline
     np_dt = np.uint8 if sc.dtype == "u8" else np.uint16
     t_dt = torch.uint8 if sc.dtype == "u8" else torch.int16          # int16 storage viewed as uint16 by numpy
     h_i0 = torch.empty((H, W), dtype=t_dt).pin_memory(); h_i1 = torch.empty((H, W), dtype=t_dt).pin_memory()
     i0_host = h_i0.numpy().view(np_dt); i1_host = h_i1.numpy().view(np_dt)
     i0_host[...] = sc.i0.cpu().numpy().astype(np_dt); i1_host[...] = sc.i1.cpu().numpy().astype(np_dt)
-    h_xy = torch.from_numpy(sc.xyuvav.copy()).pin_memory()
-    h_planes = torch.empty((5, sc.dimy, sc.dimx), dtype=torch.float32).pin_memory()
+    h_xy = torch.from_numpy(xy_band.copy()).pin_memory()
     del sc.i0, sc.i1
     torch.cuda.empty_cache()
 
-    # global (mosaic) grid for N > 1: the ranks' grids stacked along y = the bands of one grid
+    transport = None
+    comm_stats = {"halo_exchanges": 0, "allreduces": 0, "steps_counted": 0}
     if world > 1:
-        from mimc3_b200 import bands
-        gl_dimy = sc.dimy * world
-        xy_all = [None] * world
-        dist.all_gather_object(xy_all, sc.xyuvav)
-        xy_glob = np.concatenate(xy_all, axis=0)
-        # make map-y continue down the mosaic so the global grid is regular
-        for r in range(world):
-            xy_glob[r * n:(r + 1) * n, 1] -= r * sc.dimy * sc.spacing * sc.mpp
-        gparams = lib.params_for(xy_glob, sc.dimx, gl_dimy, sc.dt)
-        transport = bands.DistTransport()
-        comm_stats = {"halo_exchanges": 0, "allreduces": 0, "steps_counted": 0}
+        if args.band_comm == "nccl":
+            # the library's own communicator: rank 0's NCCL id travels over torch.distributed, every rank attaches
+            ids = [lib.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            ctx.comm_init_rank(ids[0], rank, world)
+        else:
+            transport = bands.DistTransport()
 
     dp = torch.empty((32, n, 3), dtype=torch.float32, device=dev)
     ncell = torch.empty((32, n), dtype=torch.int32, device=dev)
-    planes = torch.empty((5, sc.dimy * (world if (world > 1 and rank == 0) else 1), sc.dimx), dtype=torch.float32, device=dev)
+    want_parity = rank == 0 and world == 1 and not args.no_cpu_baseline
+    peaks = torch.empty((32, n, 2), dtype=torch.int32, device=dev) if want_parity else None
+    planes = torch.empty((5, gdimy, dimx), dtype=torch.float32, device=dev) if rank == 0 else None
+    band_planes = torch.empty((5, rows, dimx), dtype=torch.float32, device=dev) if world > 1 else None
+    plane_bytes = np.array([r * dimx * 4 for _, r in band_rows], np.int64)
     hd = pl.handles
     stream = pl.stream
 
-    def step(collect_ncell=False):
-        ctx.multimatch_async(hd["i0"], hd["i1"], hd["i0c"], hd["i1c"], offset, params, dp, ncell if collect_ncell else None)
+    def postprocess_all(d):
+        """mimc2_postprocess over the whole grid -> stats; the five planes end up in `planes` on rank 0."""
         if world == 1:
-            return ctx.postprocess(dp, sc.xyuvav, params, planes)
-        # banded postprocess: halo exchange + counter all-reduce per sweep over NCCL, then the final gather
-        band_planes, st, comm = pl.postprocess_band(dp, xy_glob, gparams, rank * sc.dimy, sc.dimy, transport)
+            return ctx.postprocess(d, gxy, gparams, planes)
+        if transport is None:
+            # banded postprocess inside the library: halo rows / dirty flags / sweep counters over NCCL on the context's
+            # stream, then the final gather of the five planes on rank 0
+            st = ctx.postprocess_band(d, gxy, gparams, row0, rows, None, band_planes)
+            for k in range(5):
+                ctx.comm_gather(band_planes[k], plane_bytes, planes[k] if rank == 0 else None, 0)
+            info = ctx.comm_info()
+            comm_stats["halo_exchanges"], comm_stats["allreduces"] = info["halo_exchanges"], info["allreduces"]
+            comm_stats["steps_counted"] += 1
+            return st
+        bp, st, comm = pl.postprocess_band(d, gxy, gparams, row0, rows, transport)
         comm_stats["halo_exchanges"] += comm.n_exchanges; comm_stats["allreduces"] += comm.n_allreduce; comm_stats["steps_counted"] += 1
         with torch.cuda.stream(stream):
-            parts = transport.gather_rows(band_planes, dst=0)
-            if rank == 0:
-                torch.cat(parts, dim=1, out=planes)
+            if len(set(r for _, r in band_rows)) == 1:
+                parts = transport.gather_rows(bp, dst=0)
+                if rank == 0:
+                    torch.cat(parts, dim=1, out=planes)
+            else:
+                raise SystemExit("bench.py: --band-comm python needs equal bands (use the default nccl communicator)")
         return st
+
+    def step(collect_ncell=False):
+        ctx.multimatch_async(hd["i0"], hd["i1"], hd["i0c"], hd["i1c"], offset, params, dp, ncell if collect_ncell else None,
+                             peaks if collect_ncell else None)
+        return postprocess_all(dp)
 
     def barrier():
         ctx.sync()
@@ -374,7 +501,16 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
-    value = n * world / (ms_per_step * 1e-3)
+    value = n_total / (ms_per_step * 1e-3)
+    # fingerprint of the five planes of the last timed step (NaNs canonicalised): identical for every N of a
+    # strong-scaling workload, i.e. the banded postprocess reproduces the single-GPU result bit for bit
+    planes_digest = None
+    if rank == 0:
+        import hashlib
+        ph = planes.cpu().numpy().copy()
+        ph[np.isnan(ph)] = np.float32(np.nan)
+        planes_digest = hashlib.sha256(ph.tobytes()).hexdigest()
+        del ph
 
     # ---- roofline of the dominant kernel -------------------------------------------------------
     peak_tf, _ = ctx.fp32_peak()
@@ -390,6 +526,9 @@ def main():
     roofline = {"bound": "fp32", "kernel": "match2_kernel<ocw,G> (exact-FP32 DLC-NCC matcher; match_kernel for nodes outside its class)", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": achieved_tf / peak_tf, "traffic": traffic,
                 "peak_source": "FP32 FMA micro-benchmark measured live on this GPU (mimc3cu_fp32_peak); MEASURED_PEAKS.json has no CUDA-core FP32 figure",
+                # driver-independent denominator: SMs x 128 FP32 lanes x 2 flop x the maximum SM clock nvidia-smi reports
+                "peak_nominal": 148 * 128 * 2 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12,
+                "frac_nominal": achieved_tf / (148 * 128 * 2 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e12),
                 "algorithmic_flop_per_step": alg_flop_step, "algorithmic_flop_per_launch": alg_flop_step / 32.0,
                 "launches_per_step": 32, "avg_launch_ms": match_ms_per_launch,
                 "kernel_share_of_step": fam_ms[0] / ms_total, "conv2_share_of_step": fam_ms[1] / ms_total,
@@ -409,31 +548,34 @@ def main():
     e2e = None
     if not args.no_e2e:
         xy_host = h_xy.numpy()
-        planes_host = (torch.empty((5, sc.dimy * world, sc.dimx), dtype=torch.float32).pin_memory().numpy()
-                       if (world > 1 and rank == 0) else h_planes.numpy())
+        planes_host = torch.empty((5, gdimy, dimx), dtype=torch.float32).pin_memory().numpy() if rank == 0 else None
+
+        cp_ms = []
 
         def e2e_step():
             pl.set_images(i0_host, i1_host)                              # H2D + on-device cast
-            d, _ = pl.match_all(xy_host, sc.dimx, sc.dimy, sc.dt, offset)   # nodes + host pivots + H2D overlapped with the attempts
+            off_e2e = offset
             if world == 1:
-                pln, _ = pl.postprocess(d)
-                ctx.finalize(pln, pl.params)
-            else:
-                band, _, _ = pl.postprocess_band(d, xy_glob, gparams, rank * sc.dimy, sc.dimy, transport)
-                with torch.cuda.stream(stream):
-                    parts = transport.gather_rows(band, dst=0)
-                    pln = torch.cat(parts, dim=1) if rank == 0 else None
-                stream.synchronize()
-                if rank == 0:
-                    ctx.finalize(pln, gparams)
+                # control-point stage (get_offset_image, MIMC_module.c:33-492) on the GPU: its offset feeds the matcher
+                tcp = time.perf_counter()
+                rc_cp, off_cp, _, _ = ctx.get_offset_image(hd["i0"], hd["i1"], xy_host, gparams, 1)
+                cp_ms.append(1e3 * (time.perf_counter() - tcp))
+                if rc_cp != 1 or tuple(off_cp) != tuple(offset):
+                    raise SystemExit(f"bench.py: control-point stage returned {rc_cp}, offset {off_cp} (scene offset {offset})")
+                off_e2e = off_cp
+            d, _ = pl.match_all(xy_host, dimx, rows, sc.dt, off_e2e)   # nodes + host pivots + H2D overlapped with the attempts
+            postprocess_all(d)
             if rank == 0:
-                ctx._ck(ctx.L.mimc3cu_memcpy_d2h(ctx.h, planes_host.ctypes.data, pln.data_ptr(), planes_host.nbytes))
+                ctx.finalize(planes, gparams)
+                ctx._ck(ctx.L.mimc3cu_memcpy_d2h(ctx.h, planes_host.ctypes.data, planes.data_ptr(), planes_host.nbytes))
                 return float(np.nanmean(planes_host[4]))
+            ctx.sync()
             return 0.0
         e2e_step()
         barrier()
         t0 = time.perf_counter()
-        e2e_steps = max(1, min(args.steps, 2))
+        e2e_steps = max(1, args.steps)
+        cp_ms.clear()
         for _ in range(e2e_steps):
             qual = e2e_step()
         barrier()
@@ -442,34 +584,38 @@ def main():
             tt = torch.tensor([dt_e2e], dtype=torch.float64, device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt_e2e = float(tt.item())
-        e2e = {"value": n * world / dt_e2e, "unit": "nodes/s",
-               "h2d_bytes_per_step": int(world * (i0_host.nbytes + i1_host.nbytes + xy_host.nbytes + pl.pivot_bytes)),
-               "d2h_bytes_per_step": int(5 * 4 * n * world), "ms_per_step": dt_e2e * 1e3, "steps": e2e_steps,
-               "timing": "host wall clock between device synchronisations, max over ranks (the leg includes host pivot generation)",
+        e2e = {"value": n_total / dt_e2e, "unit": "nodes/s",
+               "h2d_bytes_per_step": int(world * (i0_host.nbytes + i1_host.nbytes) + 6 * 8 * n_total + world * pl.pivot_bytes),
+               "d2h_bytes_per_step": int(5 * 4 * n_total), "ms_per_step": dt_e2e * 1e3, "steps": e2e_steps,
+               "timing": "host wall clock between device synchronisations, max over ranks (the leg includes the control-point stage at N=1 and host pivot generation)",
+               "cp_stage_ms": float(np.mean(cp_ms)) if cp_ms else None,
                "mean_support": qual}
 
-    # ---- CPU baseline on this box's host cores (rank 0, N = 1) ------------------------------------------
+    # ---- CPU baseline on this box's host cores (rank 0, N = 1) + parity verdict on the measured scene ---------
     cpu = None
+    parity = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        import oracle
         i0f = ctx.image_download(hd["i0"], H, W); i1f = ctx.image_download(hd["i1"], H, W)
-        filtered = []
-        zero = torch.zeros((H, W), dtype=torch.float32, device=dev)
-        for h in (hd["i0c"], hd["i1c"]):
-            ctx._ck(ctx.L.mimc3cu_image_copy_from_device(ctx.h, h, zero.data_ptr()))
-        for k in range(3):
-            ctx.conv2(hd["i0"], oracle.KERNELS[k], hd["i0c"]); ctx.conv2(hd["i1"], oracle.KERNELS[k], hd["i1c"])
-            filtered.append((ctx.image_download(hd["i0c"], H, W), ctx.image_download(hd["i1c"], H, W)))
         target = args.cpu_sample_nodes or 4 * sc.dimx
-        res = cpu_reference_sample(i0f, i1f, filtered, sc.xyuvav, sc.dimx, sc.dimy, sc.dt, offset, target)
-        cpu = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        res = cpu_reference_sample(i0f, i1f, sc.xyuvav, sc.dimx, sc.dimy, sc.dt, offset, target, keep_dp=True)
+        cpu = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "cp_stage_ms", "cp_offset")}
+        # the GPU results of the measured workload against the reference's on the sampled nodes
+        ctx.multimatch_async(hd["i0"], hd["i1"], hd["i0c"], hd["i1c"], offset, params, dp, ncell, peaks)
+        ctx.sync()
+        parity = parity_verdict(res, dp.cpu().numpy(), peaks.cpu().numpy(), ncell.cpu().numpy(), i0f, i1f, sc.xyuvav, sc.dimx,
+                                sc.dimy, sc.dt, offset, ctx, lib.params_for)
+        parity["workload"] = args.workload
+        del i0f, i1f
 
     if rank == 0:
         line = {"metric": "grid nodes matched per second", "value": value, "unit": "nodes/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
                 "dtype": "f32 (exact two-float accumulation of the float products, f64 normalisation; bit-exact vs the reference)", "data": "synthetic", "config": config,
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-                "collectives": (dict(comm_stats, backend="nccl", pattern="neighbour halo rows + int32 counter all-reduce per sweep, final gather of 5 planes") if world > 1 else None),
+                "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "collectives": (dict(comm_stats, backend="nccl", issued_by=("libmimc3cu.so (ncclSend/ncclRecv/ncclAllReduce on the context stream)" if transport is None else "bands.py callbacks over torch.distributed"),
+                                     pattern="neighbour halo rows + int32 counter all-reduce per sweep, final gather of 5 planes",
+                                     postprocess_ms_per_step=fam_ms[2] / max(1, args.steps)) if world > 1 else None),
+                "planes_sha256": planes_digest,
                 "postprocess_stats": {"dpf1_sweeps": int(stats[0]), "pseudosmoothing_sweeps": int(stats[1]), "holes_after_dpf0": int(stats[2])} if stats is not None else None}
         emit_json(line)
     pl.close()

@@ -153,6 +153,11 @@ int mimc3cu_find_ncc_peak_batch(mimc3cu_ctx *ctx, const float *refchips, int32_t
  * ncell_dev (32, n) optional. i0c/i1c are scratch images for the filtered pair. */
 int mimc3cu_multimatch_async(mimc3cu_ctx *ctx, int32_t i0, int32_t i1, int32_t i0c, int32_t i1c,
                              const int32_t *offset, const mimc3cu_params *p, float *dp_dev, int32_t *ncell_dev);
+/* Same with the integer peaks of every attempt, peak_dev (32, n, 2) on the device (may be NULL): what the reference
+ * keeps internal and the parity checks compare against the oracle. */
+int mimc3cu_multimatch_diag_async(mimc3cu_ctx *ctx, int32_t i0, int32_t i1, int32_t i0c, int32_t i1c,
+                                  const int32_t *offset, const mimc3cu_params *p, float *dp_dev, int32_t *ncell_dev,
+                                  int32_t *peak_dev);
 
 /* ---- control points --------------------------------------------------------------- */
 /* get_offset_image, MIMC_module.c:33-492: integer offset between the two images from slow
@@ -203,10 +208,32 @@ typedef struct mimc3cu_band_comm {
 int mimc3cu_band_halo(const mimc3cu_params *p);
 /* dp_dev (num_dp, own_rows*dimx, 3) of the OWNED nodes; xyuvav = the GLOBAL (dimy*dimx, 6) matrix on
  * the host; p->dimx/dimy = the GLOBAL grid; planes_dev 5 x (own_rows, dimx).  comm == NULL is only
- * valid for the single band [0, dimy) (== mimc3cu_postprocess). stats are global. */
+ * valid for the single band [0, dimy) (== mimc3cu_postprocess) or with a communicator attached to the context
+ * (mimc3cu_comm_init_*, below). stats are global. */
 int mimc3cu_postprocess_band(mimc3cu_ctx *ctx, const float *dp_dev, const double *xyuvav, const mimc3cu_params *p,
                              int32_t own_row0, int32_t own_rows, const mimc3cu_band_comm *comm, float *planes_dev,
                              int32_t *stats);
+
+/* ---- the library's own band communicator (NCCL over NVLink / NVSwitch, csrc/comm.cu) ----------------------
+ * With a communicator attached to the context, mimc3cu_postprocess_band(comm = NULL) does the three
+ * communication steps itself: grouped ncclSend/ncclRecv of the halo rows between band neighbours, the OR of the
+ * scattered dirty flags, and ncclAllReduce of the sweep counters, all enqueued on the context's stream (one host
+ * synchronisation per sweep: the read-back of the reduced counters that drives the reference's loop control).
+ * Band r of the node grid lives on rank r.  NCCL is bound at run time (libnccl.so.2; MIMC3CU_NCCL_LIB overrides).
+ *   one process per GPU : rank 0 calls mimc3cu_comm_unique_id, the caller distributes the 128 bytes (e.g. over
+ *                         torch.distributed or MPI), every rank calls mimc3cu_comm_init_rank;
+ *   one process, n GPUs : mimc3cu_comm_init_all over n contexts (the drop-in CLI, MIMC3CU_DEVICES=n); the bands'
+ *                         calls must then come from n host threads. */
+int mimc3cu_comm_unique_id(void *id128);
+int mimc3cu_comm_init_rank(mimc3cu_ctx *ctx, const void *id128, int32_t rank, int32_t world);
+int mimc3cu_comm_init_all(mimc3cu_ctx **ctxs, int32_t n);
+void mimc3cu_comm_destroy(mimc3cu_ctx *ctx);
+/* rank / world and the number of halo exchanges / all-reduces issued so far (any pointer may be NULL); non-zero
+ * without a communicator. */
+int mimc3cu_comm_info(const mimc3cu_ctx *ctx, int32_t *rank, int32_t *world, int64_t *exchanges, int64_t *allreduces);
+/* The final gather: rank r contributes bytes[r] bytes from the device buffer `send`; on `root` the device buffer
+ * `recv` receives them back to back in rank order.  Asynchronous on the context's stream. */
+int mimc3cu_comm_gather(mimc3cu_ctx *ctx, const void *send, const int64_t *bytes, void *recv, int32_t root);
 
 /* Intermediate fields of the last mimc3cu_postprocess call, copied to the host for the
  * differential tests: which = 0 dpf0 (i32), 1 dpf1 ids (i32), 2 dpf1 dx (f32), 3 dpf1 dy,

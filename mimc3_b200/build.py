@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmimc3cu.so")
 DROPIN = os.path.join(HERE, "libmimc3cu_dropin.a")
-SOURCES = ["api.cu", "match.cu", "match2.cu", "sat.cu", "cp.cu", "conv2.cu", "post.cu", "probe.cu"]
+SOURCES = ["api.cu", "match.cu", "match2.cu", "sat.cu", "cp.cu", "conv2.cu", "post.cu", "comm.cu", "probe.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 HOST_CXX = "/usr/bin/g++"
 
@@ -31,29 +31,40 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build_variant(name: str, extra_flags) -> str:
+    """Development aid: the library compiled with extra nvcc flags (e.g. -DMIMC3CU_PROFILE) into
+    libmimc3cu_<name>.so next to the product library; MIMC3CU_LIB=<path> makes lib.py load it."""
+    return build(force=True, out=os.path.join(HERE, f"libmimc3cu_{name}.so"), objdir=os.path.join(HERE, "build", name),
+                 extra=list(extra_flags), dropin=False)
+
+
+def build(force: bool = False, verbose: bool = False, out: str = LIB, objdir: str = "", extra=(), dropin: bool = True) -> str:
     if not force and not _stale():
         return LIB
     objs = []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    objdir = objdir or os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
     procs = []
     for src in SOURCES:
-        obj = os.path.join(HERE, "build", src.replace(".cu", ".o"))
-        cmd = [NVCC, *FLAGS, *os.environ.get("MIMC3CU_NVCC_EXTRA", "").split(), "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [NVCC, *FLAGS, *extra, *os.environ.get("MIMC3CU_NVCC_EXTRA", "").split(), "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:
-        out, _ = p.communicate()
+        log, _ = p.communicate()
         if verbose or p.returncode:
-            sys.stderr.write(out)
+            sys.stderr.write(log)
         if p.returncode:
             raise RuntimeError(f"nvcc failed on {src}")
-    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-ccbin", HOST_CXX, "-Xcompiler", "-pthread", "-lcudart"]
+    # linked under a temporary name and renamed: a repository snapshot (gpurun) never sees a half-written library
+    cmd = [NVCC, "-shared", "-o", out + ".tmp", *objs, "-ccbin", HOST_CXX, "-Xcompiler", "-pthread", "-lcudart", "-ldl"]
     subprocess.run(cmd, check=True)
-    build_dropin()
-    return LIB
+    os.replace(out + ".tmp", out)
+    if dropin:
+        build_dropin()
+    return out
 
 
 def build_dropin() -> str:
@@ -69,4 +80,8 @@ def build_dropin() -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--variant" in sys.argv:      # python -m mimc3_b200.build --variant prof -DMIMC3CU_PROFILE
+        i = sys.argv.index("--variant")
+        print(build_variant(sys.argv[i + 1], sys.argv[i + 2:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -34,6 +34,13 @@ int ensure_scratch(mimc3cu_ctx *ctx, size_t bytes) {
     return 0;
 }
 
+int upload_sync(mimc3cu_ctx *ctx, void *dev, const void *host, size_t bytes) {
+    if (bytes == 0) return 0;
+    CU_CHECK(ctx, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->upload_stream));
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->upload_stream));
+    return 0;
+}
+
 static cudaEvent_t take_event(mimc3cu_ctx *ctx) {
     cudaEvent_t e = nullptr;
     if (!ctx->event_pool.empty()) { e = ctx->event_pool.back(); ctx->event_pool.pop_back(); }
@@ -140,11 +147,11 @@ int mimc3cu_create(int device, mimc3cu_ctx **out) {
         return mimc3cu_fail(nullptr, "mimc3cu_create: no CUDA device available (%s); this library has no CPU fallback",
                             e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
     if (device < 0 || device >= n) return mimc3cu_fail(nullptr, "mimc3cu_create: device %d out of range (0..%d)", device, n - 1);
-    mimc3cu_ctx *ctx = new mimc3cu_ctx();
-    ctx->device = device;
     CU_CHECK(nullptr, cudaSetDevice(device));
     cudaDeviceProp prop;
     CU_CHECK(nullptr, cudaGetDeviceProperties(&prop, device));
+    mimc3cu_ctx *ctx = new mimc3cu_ctx();
+    ctx->device = device;
     if (prop.major < 10) {
         delete ctx;
         return mimc3cu_fail(nullptr, "mimc3cu_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
@@ -152,10 +159,15 @@ int mimc3cu_create(int device, mimc3cu_ctx **out) {
     }
     ctx->num_sms = prop.multiProcessorCount;
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
-    CU_CHECK(nullptr, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    CU_CHECK(nullptr, cudaMalloc(&ctx->counter, 256));
-    CU_CHECK(nullptr, cudaMalloc(&ctx->minbuf, 4096 * sizeof(float)));
-    CU_CHECK(nullptr, cudaMalloc(&ctx->statbuf, 64));
+    cudaError_t ce = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaMalloc(&ctx->counter, 256);
+    if (ce == cudaSuccess) ce = cudaMalloc(&ctx->minbuf, 4096 * sizeof(float));
+    if (ce == cudaSuccess) ce = cudaMalloc(&ctx->statbuf, 64);
+    if (ce != cudaSuccess) {
+        mimc3cu_destroy(ctx);   // releases whatever was created
+        return mimc3cu_fail(nullptr, "mimc3cu_create: %s", cudaGetErrorString(ce));
+    }
     if (const char *m = getenv("MIMC3CU_MATCHER")) {
         if (!strcmp(m, "v1") || !strcmp(m, "general")) ctx->matcher = 1;
         else if (!strcmp(m, "v2")) ctx->matcher = 2;
@@ -167,8 +179,11 @@ int mimc3cu_create(int device, mimc3cu_ctx **out) {
 void mimc3cu_destroy(mimc3cu_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    mimc3cu_comm_destroy(ctx);
     post_free(ctx);
+    for (auto &tv : ctx->timers) for (auto &pr : tv) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (auto e : ctx->event_pool) cudaEventDestroy(e);
     for (auto &im : ctx->images) if (im.used) { if (im.d) cudaFree(im.d); if (im.sat) cudaFree(im.sat); }
     for (auto &p : ctx->pivots) {
         if (p.off) cudaFree(p.off);
@@ -182,7 +197,8 @@ void mimc3cu_destroy(mimc3cu_ctx *ctx) {
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->counter) cudaFree(ctx->counter);
     if (ctx->minbuf) cudaFree(ctx->minbuf);
-    cudaStreamDestroy(ctx->stream);
+    if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
@@ -347,7 +363,7 @@ int mimc3cu_set_nodes(mimc3cu_ctx *ctx, const double *xyuvav, int32_t n) {
             uv[g].y = (int32_t)xyuvav[6 * (size_t)g + 3];
         }
     });
-    CU_CHECK(ctx, cudaMemcpy(ctx->node_uv, uv.data(), sizeof(int2) * (size_t)n, cudaMemcpyHostToDevice));
+    if (int rc = upload_sync(ctx, ctx->node_uv, uv.data(), sizeof(int2) * (size_t)n)) return rc;
     ctx->n = n;
     return 0;
 }
@@ -388,8 +404,10 @@ int mimc3cu_set_pivots(mimc3cu_ctx *ctx, int32_t slot, const int32_t *off, const
         CU_CHECK(ctx, cudaMalloc(&ps.piv, sizeof(int32_t) * 2 * (tot + tot / 8)));
         ps.piv_cap = tot + tot / 8;
     }
-    CU_CHECK(ctx, cudaMemcpy(ps.off, off, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyHostToDevice));
-    if (ps.total > 0) CU_CHECK(ctx, cudaMemcpy(ps.piv, piv, sizeof(int32_t) * 2 * (size_t)ps.total, cudaMemcpyHostToDevice));
+    // both copies are queued before the wait (the caller's arrays are pageable as a rule: staged chunk by chunk)
+    CU_CHECK(ctx, cudaMemcpyAsync(ps.off, off, sizeof(int32_t) * ((size_t)n + 1), cudaMemcpyHostToDevice, ctx->upload_stream));
+    if (int rc = upload_sync(ctx, ps.piv, piv, sizeof(int32_t) * 2 * (size_t)std::max<int64_t>(ps.total, 0))) return rc;
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->upload_stream));
     return 0;
 }
 
@@ -523,6 +541,11 @@ static const int kFilterH[3] = {1, 3, 3}, kFilterW[3] = {3, 1, 3};
 
 int mimc3cu_multimatch_async(mimc3cu_ctx *ctx, int32_t i0, int32_t i1, int32_t i0c, int32_t i1c, const int32_t *offset,
                              const mimc3cu_params *p, float *dp_dev, int32_t *ncell_dev) {
+    return mimc3cu_multimatch_diag_async(ctx, i0, i1, i0c, i1c, offset, p, dp_dev, ncell_dev, nullptr);
+}
+
+int mimc3cu_multimatch_diag_async(mimc3cu_ctx *ctx, int32_t i0, int32_t i1, int32_t i0c, int32_t i1c, const int32_t *offset,
+                                  const mimc3cu_params *p, float *dp_dev, int32_t *ncell_dev, int32_t *peak_dev) {
     if (!p || !dp_dev) return mimc3cu_fail(ctx, "multimatch: params and dp output are required");
     const size_t n = (size_t)ctx->n;
     int32_t off_rev[2] = {offset ? -offset[0] : 0, offset ? -offset[1] : 0};
@@ -544,10 +567,12 @@ int mimc3cu_multimatch_async(mimc3cu_ctx *ctx, int32_t i0, int32_t i1, int32_t i
         }
         for (int c = 0; c < 4; c++) {
             const int idx = variant * 8 + c * 2;   // dp[cnt*2] / dp[cnt*8+cntc*2+8]
-            if (int rc = mimc3cu_match_async(ctx, a, b, off_fwd, c, +1, p->vec_ocw[c], 0, dp_dev + (size_t)idx * n * 3, nullptr,
+            if (int rc = mimc3cu_match_async(ctx, a, b, off_fwd, c, +1, p->vec_ocw[c], 0, dp_dev + (size_t)idx * n * 3,
+                                             peak_dev ? peak_dev + (size_t)idx * n * 2 : nullptr,
                                              ncell_dev ? ncell_dev + (size_t)idx * n : nullptr)) return rc;
             if (int rc = mimc3cu_match_async(ctx, b, a, off_rev, c, -1, p->vec_ocw[c], 1, dp_dev + (size_t)(idx + 1) * n * 3,
-                                             nullptr, ncell_dev ? ncell_dev + (size_t)(idx + 1) * n : nullptr)) return rc;
+                                             peak_dev ? peak_dev + (size_t)(idx + 1) * n * 2 : nullptr,
+                                             ncell_dev ? ncell_dev + (size_t)(idx + 1) * n : nullptr)) return rc;
         }
     }
     return 0;

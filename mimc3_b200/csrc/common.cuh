@@ -48,11 +48,21 @@ struct PivotSet {
     } bins[2];
 };
 
+// comm.cu: NCCL communicator of the node-row bands (one rank per band)
+struct BandComm {
+    void *comm = nullptr;      // ncclComm_t
+    int rank = 0, world = 1;
+    void *tmp = nullptr;       // receive buffers of the dirty-flag OR-reduction
+    size_t tmp_bytes = 0;
+    int64_t n_exchanges = 0, n_allreduce = 0;
+};
+
 struct mimc3cu_ctx {
     int device = 0;
     int num_sms = 0;
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t upload_stream = nullptr;   // host -> device copies of nodes / pivots / node lists (upload_sync)
     std::string err;
     int64_t launches = 0;
 
@@ -78,6 +88,7 @@ struct mimc3cu_ctx {
 
     // postprocess state kept for mimc3cu_postprocess_stage
     struct Post *post = nullptr;
+    BandComm *comm = nullptr;
 
     // optional per-kernel-family event timing (0 match, 1 conv2/ingest, 2 postprocess)
     bool timing = false;
@@ -107,6 +118,11 @@ int mimc3cu_fail(mimc3cu_ctx *ctx, const char *fmt, ...);
     } while (0)
 
 int ensure_scratch(mimc3cu_ctx *ctx, size_t bytes);
+// Host -> device copy that has LANDED when the call returns, without waiting for the work queued on ctx->stream.
+// (cudaMemcpy on the legacy stream is not ordered against the non-blocking context stream, and for pageable
+// sources it may return once the data is staged; kernels launched afterwards could then read stale buffers.)
+// The caller guarantees that no kernel in flight still reads `dev`.
+int upload_sync(mimc3cu_ctx *ctx, void *dev, const void *host, size_t bytes);
 Image *get_image(mimc3cu_ctx *ctx, int32_t handle);
 
 // match.cu
@@ -156,6 +172,12 @@ int launch_conv2(mimc3cu_ctx *ctx, const float *src, int32_t H, int32_t W, const
                  int32_t kw, float *dst);
 int launch_cast_u8(mimc3cu_ctx *ctx, const uint8_t *src, float *dst, size_t count);
 int launch_cast_u16(mimc3cu_ctx *ctx, const uint16_t *src, float *dst, size_t count);
+
+// comm.cu (all asynchronous on ctx->stream; local rows [own0, own1) are owned, `halo` rows on either side are the neighbours')
+int bandcomm_halo_exchange(mimc3cu_ctx *ctx, void *const *arrays, const int32_t *elem_bytes, int32_t count, int dimx, int rows,
+                           int own0, int own1, int halo);
+int bandcomm_halo_or_reduce(mimc3cu_ctx *ctx, uint8_t *flags, int dimx, int rows, int own0, int own1, int halo);
+int bandcomm_allreduce_sum(mimc3cu_ctx *ctx, int32_t *dev_vals, int32_t count);
 
 // post.cu
 int post_cluster(mimc3cu_ctx *ctx, const float *dp, int32_t n, int32_t num_dp, float *mvn, int32_t *ncl);

@@ -47,14 +47,15 @@
 namespace {
 
 constexpr int kThreads = 256;
-constexpr unsigned char kComputed = 1, kVisible = 2, kListed = 4;
-// job word: cy << 16 | cx; bit 31 marks a speculative cell (evaluated ahead of the reference's order because
-// the climb is about to ask for it; skipped instead of re-evaluated when it would need the masked path)
-constexpr int kSpec = (int)0x80000000;
+// per-cell state.  cval[] holds kUnknownBits (a NaN no computation produces) until the cell has been evaluated;
+// cflag[]: kVisible = the reference's state machine has "evaluated" the cell (cmap >= -1, MIMC_module.c:713),
+// kListed = queued for evaluation; ctab[]: kTabComplete | k once all nine cells of the 3x3 probe centred here
+// are known, k = scan index (u outer, v inner, :709-741) of the first occurrence of their maximum.
+constexpr unsigned char kVisible = 2, kListed = 4, kTabComplete = 0x10;
+constexpr unsigned int kUnknownBits = 0x7fc0deadu;
+constexpr int kWalkDone = 1 << 30;
 __device__ __forceinline__ int job_cy(int job) { return (job >> 16) & 0x7fff; }
 __device__ __forceinline__ int job_cx(int job) { return job & 0xffff; }
-constexpr int kMaxJobsCap = 64;   // upper bound of cells per evaluation round (Cfg::MAXJ is per chip size)
-constexpr int kPivCache = 64;
 
 struct Match2Args {
     const float *ref, *srch;
@@ -81,12 +82,15 @@ struct Match2Args {
     unsigned int A0_bits, Mlo_bits;
     double hi_unit, lo_unit;
     float min_dn;
+    int num_sms;                    // leader-warp rotation: co-resident CTAs lead from different SM sub-partitions
 };
 
 #ifdef MIMC3CU_PROFILE
-__device__ unsigned long long g_prof[8];   // cycles: 0 node total, 1 staging, 2 produce, 3 compute(+wait), 4 finalize, 5 rounds, 6 nodes
+// cycles seen by lane 0 of the group's leader warp: 0 node total, 1 staging, 2 leader section (7 walk, 8 requests, 9 replay + fit),
+// 3 compute (+ barrier waits), 4 finalize + masked round, 10 probe-table update; 5 rounds, 6 nodes
+__device__ unsigned long long g_prof[16];
 #define PROF_T(var) const long long var = clock64()
-#define PROF_ADD(slot, v) do { if (t == 0) atomicAdd(&g_prof[slot], (unsigned long long)(v)); } while (0)
+#define PROF_ADD(slot, v) do { if (lane == 0 && gwarp == lead) atomicAdd(&g_prof[slot], (unsigned long long)(v)); } while (0)
 #else
 #define PROF_T(var)
 #define PROF_ADD(slot, v)
@@ -105,24 +109,26 @@ struct Sums {
 // ocw 40: one 256-thread CTA per node, four per SM at 64 registers; its wider-search-area bins run 128-thread CTAs
 // (two chip rows per thread, three per SM) or 256-thread CTAs compiled for two per SM (no register pressure).
 // The 256-thread instantiations of ocw 7/15 only serve bins with <= 3 CTAs per SM.
-constexpr int min_ctas(int ocw, int G) { return G == 256 && ocw < 30 ? 3 : (ocw == 15 ? 2 : (ocw == 30 ? 3 : (G == 128 ? 3 : 4))); }
+constexpr int min_ctas(int ocw, int G) { return G == 64 ? 2 : (G == 256 && ocw < 30 ? 3 : (ocw == 15 ? 2 : (ocw == 30 ? 3 : (G == 128 ? 3 : 4)))); }
 
 template <int OCW, int G>
 struct Cfg {
     static constexpr int S = 2 * OCW + 1;
     // A thread keeps RB chip rows (r, r + RPT, ...) of one column segment: RB = 2 lets half as many threads
     // hold the 81x81 chip (54 pixels each), which is what fits five nodes into an SM's register file.
-    static constexpr int RB = (OCW == 40 && G == 128) ? 2 : 1;
+    static constexpr int RB = ((OCW == 40 && G == 128) || (OCW == 30 && G == 64)) ? 2 : 1;
     static constexpr int RPT = (S + RB - 1) / RB;            // rows per row block
     static constexpr int NSEG = (G / RPT) < S ? (G / RPT) : S;   // row segments per chip row (at most one pixel each)
     static constexpr int L = (S + NSEG - 1) / NSEG;
-    static constexpr int NGROUPS = RB == 2 ? 1 : kThreads / G;   // groups (nodes) per CTA
+    static constexpr int NGROUPS = (OCW == 40 && G == 128) ? 1 : kThreads / G;   // groups (nodes) per CTA
     static constexpr int CTA = G * NGROUPS;
     static constexpr int NWARPS = G / 32;
-    // cells per evaluation round: one slot per lane of the finalizing warp.  (64, so that the ~39 first-probe cells
-    // of a static node go in one round, costs ten more live registers in the compute loop: 5 % slower at ocw 40.)
-    static constexpr int MAXJ = 32;
-    static constexpr int NH = MAXJ / 32;
+    // cells per evaluation round: thread c of the group owns cell c (SAT look-up, normalisation), so the ~39
+    // first-probe cells of a static node go in one round wherever a group has 64 threads
+    static constexpr int MAXJ = G == 32 ? 32 : 64;
+    // pivots per node this instantiation can walk (explore state in shared memory); longer pivot lines go to
+    // a wider instantiation or to the general kernel
+    static constexpr int PMAX = G == 32 ? 64 : 128;
     static_assert(NSEG >= 1, "group too small for this chip");
     static_assert((L + 1) / 2 <= 16, "at most 16 pixels per FP32 accumulator");
 };
@@ -239,22 +245,24 @@ __device__ void subpixel_fit(const float n9[9], int peak_du, int peak_dv, float 
 }
 
 // Per-group control block in shared memory.
-template <int NWARPS, int MAXJ>
+template <int NWARPS, int MAXJ, int PMAX>
 struct Ctl {
-    int job[MAXJ];                   // cells of the current round
+    int job[MAXJ];                   // cells of the current round: cy << 16 | cx
+    int slowjob[MAXJ];               // cells of the round that need the masked (null-excluding) evaluation
     int2 part[NWARPS][MAXJ];         // per-warp integer partial sums (hi units, lo units)
     Sums partd[NWARPS];              // masked-path partials
-    int2 pivc[kPivCache];       // the node's first pivots (the state machine walks them serially)
-    // Node geometry and the climb state live HERE, not in registers: only the leader warp needs
-    // them, and only between evaluation rounds; keeping them out of the register file of the
-    // compute loop is what lets the 81x81 instantiation keep its chip pixels without remat/spills.
-    struct Geo { int g, P, su0, sv0, dx2, dy2, Dx2, Dy2, cw, ch, sa_elems, cell_elems; const int2 *piv; } geo;
-    struct Climb {
-        int ip_batch, phase, ip, px, py, duv0, duv1, flag_new, peak_x, peak_y, ncells, in_pivot, nslow;
-        float nccmax, best;
-    } st;
-    int m;                      // >0 fast round, <0 done, 0 unused
-    int mode;                   // 0 fast round, 1 masked round
+    // explore state of every pivot (cell coordinates cx | cy << 15 | kWalkDone, running maximum) and where it started
+    int wpos[PMAX], wstart[PMAX];
+    float wmax[PMAX];
+    // Node geometry lives HERE, not in registers: only the leader warp needs it, and only between evaluation rounds;
+    // keeping it out of the register file of the compute loop is what lets the 81x81 instantiation keep its chip
+    // pixels without remat/spills.
+    struct Geo { int g, P, su0, sv0, dx2, dy2, Dx2, Dy2, cw, ch, sa_elems, cell_elems; } geo;
+    int blk[PMAX];              // probe centres (cell index) of the pivots blocked in this round
+    int nblk;
+    int m;                      // cells requested for this round (may exceed MAXJ: the excess is not listed)
+    int nslow;                  // cells in slowjob[]
+    int bbox[4];                // cx0, cx1, cy0, cy1 of the round's cells (probe table update)
     unsigned int node[2];       // dynamic node fetch, double-buffered: the next index is fetched a node ahead
     int valid;
     // chip constants from the reference SAT
@@ -263,379 +271,319 @@ struct Ctl {
     int chip_fast;
 };
 
-// Evaluation rounds of one node: driven by warp 0 of the group (the reference's state machine),
-// executed by all of the group's threads.  Geometry and climb state are read from / written to the
-// control block inside the leader-only sections, so the compute loop keeps only the chip pixels,
-// the tile pointer and the pitch in registers.
+// Evaluation rounds of one node.  The reference's climb (MIMC_module.c:691-753) asks for NCC cells one 3x3 probe
+// at a time, pivot after pivot; a round per probe would leave the group idle behind a serial state machine.
+// Instead (oracle/leader_model.c restates this schedule on the CPU and the test-suite asserts that it is
+// equivalent to the reference's):
+//   explore  lane i of the leader warp walks pivot i's climb on the values known so far, ignoring the
+//            reference's "nothing new in this probe => stop" rule -- that rule can only SHORTEN a path, so the
+//            walked cells are a superset of the reference's (by +0.1 %).  One step is a look-up in the probe
+//            table ctab (all nine cells known?  where is their maximum?), which all threads keep up to date
+//            after every round.  A pivot whose next probe has unknown cells is blocked and lists them; the
+//            lists of all blocked pivots form one evaluation round (<= MAXJ cells).
+//   replay   once no pivot is blocked the reference's state machine runs verbatim over the known values and
+//            decides visibility, the evaluated-cell count, the peak and its NCC.
+// 4.4 rounds per node instead of 7.5 (fast glaciers: 9 instead of ~38), and no speculative cells.
 template <int OCW, int G, bool EXACTP, typename CtlT>
 __device__ __forceinline__ void node_rounds(const Match2Args &a, CtlT &ctl, float *sa, const float *sa_thread,
                                             const float (&chip)[Cfg<OCW, G>::RB][Cfg<OCW, G>::L], const int pitch, const int row2, const bool active, const int t,
-                                            const int lane, const int gwarp) {
+                                            const int lane, const int gwarp, const int lead) {
     using C = Cfg<OCW, G>;
     constexpr int S = C::S, L = C::L;
     const int W1 = a.W + 1;
-    {
-        for (;;) {
-            PROF_T(t_p0);
-            if (gwarp == 0) {
-                // geometry + climb state: shared memory -> registers for the duration of this block only
-                const int P = ctl.geo.P, dx2 = ctl.geo.dx2, dy2 = ctl.geo.dy2, Dx2 = ctl.geo.Dx2, Dy2 = ctl.geo.Dy2, cw = ctl.geo.cw;
-                const int2 *piv = ctl.geo.piv;
-                float *cval = sa + ctl.geo.sa_elems;
-                unsigned char *cflag = (unsigned char *)(cval + ctl.geo.cell_elems);
-                int ip_batch = ctl.st.ip_batch, phase = ctl.st.phase, ip = ctl.st.ip, px = ctl.st.px, py = ctl.st.py;
-                int duv0 = ctl.st.duv0, duv1 = ctl.st.duv1, flag_new = ctl.st.flag_new, peak_x = ctl.st.peak_x, peak_y = ctl.st.peak_y;
-                int ncells = ctl.st.ncells, nslow = ctl.st.nslow;
-                bool in_pivot = ctl.st.in_pivot != 0;
-                float nccmax = ctl.st.nccmax, best = ctl.st.best;
-                __syncwarp();
-                int m = 0, mode = 0;
-                if (nslow > 0) {
-                    // masked re-evaluation of the cells the fast path could not take
-                    mode = 1; m = nslow;   // ctl.job[0..nslow) was filled by the finalize step below
-                    nslow = 0;
-                } else {
-                    if (phase == 0) {
-                        while (ip_batch < P && m <= C::MAXJ - 9) {
-                            const int2 pv = ip_batch < kPivCache ? ctl.pivc[ip_batch] : piv[ip_batch];
-                            const int bx = a.sign * pv.x + dx2, by = a.sign * pv.y + dy2;
-                            ip_batch++;
-                            if (bx - OCW <= 1 || bx + OCW >= Dx2 - 1 || by - OCW <= 1 || by + OCW >= Dy2 - 1) continue;
-                            bool want = false;
-                            int cell = 0;
-                            if (lane < 9) {
-                                cell = (by + (lane % 3 - 1) - OCW - 1) * cw + (bx + (lane / 3 - 1) - OCW - 1);
-                                want = !(cflag[cell] & (kComputed | kListed));
-                            }
-                            const unsigned int wm = __ballot_sync(0xffffffffu, want);
-                            if (want) {
-                                ctl.job[m + __popc(wm & ((1u << lane) - 1u))] = ((by + (lane % 3 - 1) - OCW - 1) << 16) | (bx + (lane / 3 - 1) - OCW - 1);
-                                cflag[cell] |= kListed;
-                            }
-                            m += __popc(wm);
-                            __syncwarp();
-                        }
-                        if (m == 0 && ip_batch >= P) phase = 2;
-                    }
-                    if (phase == 2) {
-                        // Second probes of all pivots in one round.  After its first probe every pivot steps to the
-                        // arg-max of its 3x3 (a pure function of the values now in the map) and probes there; one
-                        // pivot after the other that is one small round per pivot.  Here lane i predicts pivot i's
-                        // step and the union of the cells those probes will ask for is evaluated at once.  Only
-                        // the evaluation is moved forward: visibility, counts and the climb itself stay with the
-                        // state machine below, which then finds the cells already computed.
-                        phase = 1;
-                        if (ctl.chip_fast) {
-                            for (int base = 0; base < P && m <= C::MAXJ - 9; base += 32) {
-                                const int i = base + lane;
-                                int ccx = -1, ccy = 0;   // centre of the predicted probe, in cell coordinates
-                                if (i < P) {
-                                    const int2 pv = i < kPivCache ? ctl.pivc[i] : piv[i];
-                                    const int bx = a.sign * pv.x + dx2, by = a.sign * pv.y + dy2;
-                                    if (!(bx - OCW <= 1 || bx + OCW >= Dx2 - 1 || by - OCW <= 1 || by + OCW >= Dy2 - 1)) {
-                                        float top = -2.0f;
-                                        int d0 = 0, d1 = 0;
-                                        const float *cv = cval + (by - OCW - 1) * cw + (bx - OCW - 1);
-#pragma unroll
-                                        for (int k = 0; k < 9; k++) {
-                                            const float v = cv[(k % 3 - 1) * cw + (k / 3 - 1)];
-                                            if (v > top) { top = v; d0 = k / 3 - 1; d1 = k % 3 - 1; }
-                                        }
-                                        const int nx = bx + d0, ny = by + d1;
-                                        if ((d0 | d1) != 0 && !(nx - OCW <= 1 || nx + OCW >= Dx2 - 1 || ny - OCW <= 1 || ny + OCW >= Dy2 - 1)) {
-                                            ccx = nx - OCW - 1; ccy = ny - OCW - 1;
-                                        }
-                                    }
-                                }
-                                // one lane per distinct probe centre
-                                const unsigned int peers = __match_any_sync(0xffffffffu, ccx < 0 ? -1 - lane : ((ccy << 16) | ccx));
-                                const bool owner = ccx >= 0 && (__ffs(peers) - 1) == lane;
-#pragma unroll 1
-                                for (int k = 0; k < 9; k++) {
-                                    const int cy = ccy + (k % 3 - 1), cx = ccx + (k / 3 - 1);
-                                    const bool want = owner && !(cflag[cy * cw + cx] & (kComputed | kListed));
-                                    const unsigned int wm = __ballot_sync(0xffffffffu, want);
-                                    const int pos = m + __popc(wm & ((1u << lane) - 1u));
-                                    if (want && pos < C::MAXJ) {
-                                        ctl.job[pos] = kSpec | (cy << 16) | cx;
-                                        cflag[cy * cw + cx] |= kListed;
-                                    }
-                                    m = min(m + __popc(wm), C::MAXJ);
-                                    __syncwarp();
-                                }
-                            }
-                        }
-                    }
-                    if (phase == 1 && m == 0) {
-                        // the reference's state machine, MIMC_module.c:691-753
-                        for (;;) {
-                            if (!in_pivot) {
-                                if (ip >= P) { m = -1; break; }
-                                const int2 pv = ip < kPivCache ? ctl.pivc[ip] : piv[ip];
-                                px = a.sign * pv.x + dx2; py = a.sign * pv.y + dy2;   // :693-694
-                                nccmax = -2.0f; duv0 = -1; duv1 = -1; flag_new = 1;
-                                in_pivot = true;
-                            }
-                            bool stop = !((duv0 != 0 || duv1 != 0) && flag_new != 0);       // :699
-                            if (!stop && (px - OCW <= 1 || px + OCW >= Dx2 - 1 || py - OCW <= 1 || py + OCW >= Dy2 - 1)) {
-                                duv0 = 0; duv1 = 0; stop = true;                             // :701-707 (break)
-                            }
-                            if (stop) {
-                                if (nccmax > best) { peak_x = px; peak_y = py; best = nccmax; }   // :747-752
-                                in_pivot = false; ip++;
-                                continue;
-                            }
-                            // lane k < 9 looks at probe cell k = (c1+1)*3 + (c2+1)  (c1: u outer, c2: v inner)
-                            int cell = 0;
-                            unsigned char f = kComputed;
-                            float v = 0.0f;
-                            if (lane < 9) {
-                                cell = (py + (lane % 3 - 1) - OCW - 1) * cw + (px + (lane / 3 - 1) - OCW - 1);
-                                f = cflag[cell];
-                                v = cval[cell];
-                            }
-                            const bool need = !(f & (kVisible | kComputed));
-                            const unsigned int nm = __ballot_sync(0xffffffffu, need);
-                            if (nm) {
-                                if (need) ctl.job[__popc(nm & ((1u << lane) - 1u))] = ((py + (lane % 3 - 1) - OCW - 1) << 16) | (px + (lane / 3 - 1) - OCW - 1);
-                                m = __popc(nm);
-                                break;
-                            }
-                            const bool isnew = lane < 9 && (!(f & kVisible) || v < -1.0f);   // `cmap < -1.0` => evaluated now, :713
-                            const unsigned int newm = __ballot_sync(0xffffffffu, isnew);
-                            if (isnew) cflag[cell] = f | kVisible;
-                            flag_new = __popc(newm); ncells += flag_new;
-                            // :736-741: sequential strict `>` scan == first occurrence of the maximum, taken
-                            // only if it beats the running nccmax (NaN never wins)
-                            duv0 = 0; duv1 = 0;
-                            {
-                                const unsigned int key = lane < 9 ? ordered_key(v) : 0u;
-                                const unsigned int mx = __reduce_max_sync(0xffffffffu, key);
-                                const int kb = __ffs(__ballot_sync(0xffffffffu, lane < 9 && key == mx)) - 1;
-                                const float vb = __shfl_sync(0xffffffffu, v, kb);
-                                if (vb > nccmax) { nccmax = vb; duv0 = kb / 3 - 1; duv1 = kb % 3 - 1; }
-                            }
-                            px += duv0; py += duv1;                                            // :744-745
-                            __syncwarp();
-                        }
-                    }
-                }
-                if (lane == 0) {
-                    ctl.m = m; ctl.mode = mode;
-                    ctl.st = {ip_batch, phase, ip, px, py, duv0, duv1, flag_new, peak_x, peak_y, ncells, in_pivot ? 1 : 0, nslow, nccmax, best};
-                }
+    const int cw = ctl.geo.cw, ch = ctl.geo.ch;
+    float *cval = sa + ctl.geo.sa_elems;
+    unsigned char *cflag = (unsigned char *)(cval + ctl.geo.cell_elems);
+    unsigned char *ctab = cflag + ctl.geo.cell_elems;
+    for (;;) {
+        PROF_T(t_p0);
+        // ---- explore: thread i walks pivot i as far as the probe table allows ------------------------------
+        const int P = ctl.geo.P;
+        if (t == 0) { ctl.bbox[0] = 0x7fff; ctl.bbox[1] = 0; ctl.bbox[2] = 0x7fff; ctl.bbox[3] = 0; }
+        for (int i = t; i < P; i += G) {
+            const int st = ctl.wpos[i];
+            if (st & kWalkDone) continue;
+            int cx = st & 0x7fff, cy = (st >> 15) & 0x7fff;
+            float nmax = ctl.wmax[i];
+            bool done = false;
+            for (;;) {
+                if ((unsigned)(cx - 1) > (unsigned)(cw - 3) || (unsigned)(cy - 1) > (unsigned)(ch - 3)) { done = true; break; }   // :701-707
+                const unsigned char e = ctab[cy * cw + cx];
+                if (!(e & kTabComplete)) break;                  // blocked: some of the nine cells are unknown
+                const int k = e & 15;
+                const int nx = cx + k / 3 - 1, ny = cy + k % 3 - 1;
+                const float v = cval[ny * cw + nx];
+                if (!(v > nmax)) { done = true; break; }      // nothing beats the running maximum: duv = 0
+                nmax = v;
+                if (k == 4) { done = true; break; }            // the maximum is the centre: duv = 0
+                cx = nx; cy = ny;
             }
-            PROF_T(t_p1);
-            PROF_ADD(2, t_p1 - t_p0);
-            gsync<G>();
-            const int m = ctl.m, mode = ctl.mode;
-            if (m < 0) break;
-            PROF_ADD(5, 1);
-            if (m == 0) continue;   // batch produced nothing new; warp 0 switches to the climb
-
-            if (mode == 0) {
-                // ---- fast round: sum(fl(r*s)) for m cells, exact in FP32 ------------------------------
-                // SAT corner loads for cell `lane` are issued first so their latency hides behind the loop
-                // per slot: sum(fl(s*s)), packed (sum(s) << 24 | nulls), flags = inside | (tx + 2*ty) << 1 where
-                // tx/ty say that the window reaches the never-written last column / row of the search area
-                unsigned long long w_ss[C::NH], w_pk[C::NH];
-                int w_flag[C::NH];
-#pragma unroll
-                for (int h = 0; h < C::NH; h++) { w_ss[h] = 0; w_pk[h] = 1; w_flag[h] = 0; }
-                if (gwarp == 0) {
-                    const int su0 = ctl.geo.su0, sv0 = ctl.geo.sv0, dx2 = ctl.geo.dx2, dy2 = ctl.geo.dy2, Dx2 = ctl.geo.Dx2, Dy2 = ctl.geo.Dy2;
-#pragma unroll
-                    for (int h = 0; h < C::NH; h++) {
-                        const int slot = lane + 32 * h;
-                        if (slot < m) {
-                            const int job = ctl.job[slot];
-                            const int cy = job_cy(job), cx = job_cx(job);
-                            const int x0 = cx + 1, y0 = cy + 1;                       // window origin in the search area
-                            const int ix0 = su0 - dx2 + x0, iy0 = sv0 - dy2 + y0;     // ... and in the image
-                            // The last column / row of the search area is never written by the reference
-                            // (H1): those pixels are nulls, i.e. the joint mask simply drops the chip's last
-                            // column / row.  The FP32 loop already sees zeros there; only the SAT rectangles
-                            // and n shrink.
-                            const int tx = (x0 + S - 1 == Dx2 - 1), ty = (y0 + S - 1 == Dy2 - 1);
-                            const bool inside = ix0 >= 0 && iy0 >= 0 && ix0 + S - tx <= a.W && iy0 + S - ty <= a.H;
-                            w_flag[h] = (inside ? 1 : 0) | ((tx + 2 * ty) << 1);
-                            if (inside) rect_query_packed(a.sat_srch, W1, ix0, iy0, ix0 + S - tx, iy0 + S - ty, w_ss[h], w_pk[h]);
-                        }
+            ctl.wpos[i] = cx | (cy << 15) | (done ? kWalkDone : 0);
+            ctl.wmax[i] = nmax;
+            if (!done) ctl.blk[atomicAdd(&ctl.nblk, 1)] = cy * cw + cx;
+        }
+        PROF_T(t_w1);
+        PROF_ADD(7, t_w1 - t_p0);
+        gsync<G>();
+        const int nblk = ctl.nblk;
+        if (nblk == 0) {
+            // ---- replay: the reference's state machine, MIMC_module.c:691-753, on the known values ---------
+            // (the other warps wait for the leader at the group barrier that opens the next node)
+            if (gwarp == lead) {
+                PROF_T(t_r0);
+                const int dx2 = ctl.geo.dx2, dy2 = ctl.geo.dy2;
+                int pkx = dx2 - OCW - 1, pky = dy2 - OCW - 1, ncells = 0;
+                float best = -2.0f;
+                // lane k < 9 looks at probe cell k = (c1+1)*3 + (c2+1)  (c1: u outer, c2: v inner)
+                const int loff = lane < 9 ? (lane % 3 - 1) * cw + (lane / 3 - 1) : 0;
+                for (int ip = 0; ip < P; ip++) {
+                    const int st = ctl.wstart[ip];
+                    int cx = st & 0x7fff, cy = st >> 15;                                  // :693-694
+                    float nccmax = -2.0f;
+                    for (;;) {   // one iteration per probe (:699-745); every exit leaves (cx, cy) where the reference's loop ends
+                        if ((unsigned)(cx - 1) > (unsigned)(cw - 3) || (unsigned)(cy - 1) > (unsigned)(ch - 3)) break;   // :701-707
+                        const int pos = cy * cw + cx;
+                        const unsigned char f = cflag[pos + loff];
+                        const float v = cval[pos + loff];
+                        const int k = ctab[pos] & 15;
+                        const bool isnew = lane < 9 && (!(f & kVisible) || v < -1.0f);   // `cmap < -1.0` => evaluated now, :713
+                        const unsigned int newm = __ballot_sync(0xffffffffu, isnew);
+                        if (isnew) cflag[pos + loff] = f | kVisible;
+                        ncells += __popc(newm);
+                        // :736-741: sequential strict `>` scan == first occurrence of the maximum, taken only if it
+                        // beats the running nccmax (NaN never wins)
+                        const float vb = __shfl_sync(0xffffffffu, v, k);
+                        if (!(vb > nccmax)) break;                                         // duv = 0
+                        nccmax = vb;
+                        if (k == 4) break;                                                 // duv = 0
+                        cx += k / 3 - 1; cy += k % 3 - 1;                                  // :744-745
+                        if (newm == 0) break;                                              // flag_newncc == 0, :699
                     }
-                }
-                for (int c = 0; c < m; c++) {
-                    const int job = ctl.job[c];
-                    const int cy = job_cy(job), cx = job_cx(job);
-                    unsigned int hi = 0;
-                    int lo = 0;
-#pragma unroll
-                    for (int rb = 0; rb < C::RB; rb++) {
-                        // threads without chip pixels (r = col0 = 0, chip all zero) run the same code: no branch; a
-                        // thread whose second row does not exist reads its first row again (times zero)
-                        const float *sp = sa_thread + (cy + 1) * pitch + (cx + 1) + (rb ? row2 : 0);
-                        // Two pixels per instruction (FMUL2 / FADD2 / FFMA2, sm_100): lane 0 of the packed pair
-                        // accumulates the even pixels, lane 1 the odd ones -- the same two accumulators as a
-                        // scalar loop would keep, at half the issue slots.  One accumulator pair per chip row
-                        // (<= 16 pixels per accumulator).
-                        f32x2 acc = pack2(a.A0, a.A0), lo2 = pack2(a.Mlo, a.Mlo);
-#pragma unroll
-                        for (int k = 0; k < L; k += 2) {
-                            // an odd L ends with a (pixel, 0) pair: the zero is a literal, not a load
-                            const f32x2 rv = pack2(chip[rb][k], k + 1 < L ? chip[rb][k + 1] : 0.0f);
-                            const f32x2 sv = pack2(sp[k], k + 1 < L ? sp[k + 1] : 0.0f);
-                            if (EXACTP) {
-                                // every product is exact in FP32 (scaled operands < 2^12): fma(r, s, acc) ==
-                                // fadd(acc, fmul(r, s)) and fma(r, s, -z) == p - z, one instruction less per pixel
-                                const f32x2 s1 = fma2(rv, sv, acc);
-                                const f32x2 nz = sub2(acc, s1);
-                                lo2 = add2(lo2, fma2(rv, sv, nz));
-                                acc = s1;
-                            } else {
-                                const f32x2 pr = mul2(rv, sv);
-                                const f32x2 s1 = add2(acc, pr);
-                                const f32x2 z = sub2(s1, acc);
-                                lo2 = add2(lo2, sub2(pr, z));
-                                acc = s1;
-                            }
-                        }
-                        float acc0, acc1, lo0, lo1;
-                        unpack2(acc, acc0, acc1);
-                        unpack2(lo2, lo0, lo1);
-                        hi += (__float_as_uint(acc0) - a.A0_bits) + (__float_as_uint(acc1) - a.A0_bits);
-                        lo += (int)(__float_as_uint(lo0) - a.Mlo_bits) + (int)(__float_as_uint(lo1) - a.Mlo_bits);
-                    }
-                    hi = __reduce_add_sync(0xffffffffu, hi);
-                    lo = __reduce_add_sync(0xffffffffu, lo);
-                    if (lane == 0) ctl.part[gwarp][c] = make_int2((int)hi, lo);
-                }
-                gsync<G>();
-                PROF_T(t_c1);
-                PROF_ADD(3, t_c1 - t_p1);
-                // ---- finalize: lane c of warp 0 normalises cell c --------------------------------------
-                if (gwarp == 0) {
-                    const int cw = ctl.geo.cw;
-                    float *cval = sa + ctl.geo.sa_elems;
-                    unsigned char *cflag = (unsigned char *)(cval + ctl.geo.cell_elems);
-                    int nslow = 0;
-                    int jobs[C::NH];
-                    bool slowc[C::NH];
-#pragma unroll
-                    for (int h = 0; h < C::NH; h++) { jobs[h] = 0; slowc[h] = false; }
-#pragma unroll
-                    for (int h = 0; h < C::NH; h++) {
-                        const int slot = lane + 32 * h;
-                        if (slot < m) {
-                            jobs[h] = ctl.job[slot];
-                            const int cell = job_cy(jobs[h]) * cw + job_cx(jobs[h]);
-                            const int trim = w_flag[h] >> 1;
-                            if (ctl.chip_fast && (w_flag[h] & 1) && (w_pk[h] & 0xffffffull) == 0) {
-                                long long hs = 0, ls = 0;
-#pragma unroll
-                                for (int w = 0; w < C::NWARPS; w++) {
-                                    const int2 q = ctl.part[w][slot];
-                                    hs += (unsigned int)q.x; ls += q.y;
-                                }
-                                Sums s;
-                                s.n = (S - (trim & 1)) * (S - (trim >> 1));
-                                s.sxy = (double)hs * a.hi_unit + (double)ls * a.lo_unit;
-                                s.sx = (double)ctl.chip_s[trim] * a.inv_ref; s.sxx = (double)ctl.chip_ss[trim] * a.inv_ref2;
-                                s.sy = (double)(w_pk[h] >> 24) * a.inv_srch; s.syy = (double)w_ss[h] * a.inv_srch2;
-                                cval[cell] = ncc_from_sums(s);
-                                cflag[cell] |= kComputed;
-                            } else {
-                                slowc[h] = !(jobs[h] & kSpec);   // a speculative cell is dropped; the climb asks again if it matters
-                            }
-                        }
-                    }
-                    // slow cells are compacted in place: the target index never exceeds the slot it came from
-#pragma unroll
-                    for (int h = 0; h < C::NH; h++) {
-                        const unsigned int smh = __ballot_sync(0xffffffffu, slowc[h]);
-                        __syncwarp();
-                        if (slowc[h]) ctl.job[nslow + __popc(smh & ((1u << lane) - 1u))] = jobs[h];
-                        nslow += __popc(smh);
-                        __syncwarp();
-                    }
-                    if (lane == 0) ctl.st.nslow = nslow;
+                    if (nccmax > best) { pkx = cx; pky = cy; best = nccmax; }             // :747-752
                     __syncwarp();
                 }
-                PROF_T(t_f1);
-                PROF_ADD(4, t_f1 - t_c1);
-            } else {
-                // ---- masked round: the reference's 5-sum loop with null exclusion (:719-733), FP64 ------
-                float *cval = sa + ctl.geo.sa_elems;
-                unsigned char *cflag = (unsigned char *)(cval + ctl.geo.cell_elems);
-                for (int c = 0; c < m; c++) {
-                    const int job = ctl.job[c];
-                    const int cy = job_cy(job), cx = job_cx(job);
-                    const int cell = cy * ctl.geo.cw + cx;
-                    Sums s = {0.0, 0.0, 0.0, 0.0, 0.0, 0};
-#pragma unroll
-                    for (int rb = 0; rb < C::RB; rb++) {
-                        if (!active) break;
-                        const float *sp = sa_thread + (cy + 1) * pitch + (cx + 1) + (rb ? row2 : 0);
-#pragma unroll
-                        for (int k = 0; k < L; k++) {
-                            const float rv = chip[rb][k], sv = sp[k];
-                            if (rv >= a.min_dn && sv >= a.min_dn) {   // null exclusion, :723
-                                s.n++;
-                                s.sx += (double)rv; s.sy += (double)sv;
-                                s.sxx += (double)__fmul_rn(rv, rv);
-                                s.syy += (double)__fmul_rn(sv, sv);
-                                s.sxy += (double)__fmul_rn(rv, sv);
+                // ---- sub-pixel fit and output (:757-788) -------------------------------------------------
+                if (lane == 0) {
+                    const int g = ctl.geo.g;
+                    float n9[9];
+                    for (int rr = 0; rr < 3; rr++)
+                        for (int cc = 0; cc < 3; cc++) {
+                            const int cx = pkx - 1 + cc, cy = pky - 1 + rr;
+                            float v = -2.0f;   // never evaluated (or outside the evaluable region)
+                            if (cx >= 0 && cx < cw && cy >= 0 && cy < ch) {
+                                const int cell = cy * cw + cx;
+                                if (cflag[cell] & kVisible) v = cval[cell];
                             }
+                            n9[rr * 3 + cc] = v;
                         }
-                    }
-                    s.n = __reduce_add_sync(0xffffffffu, s.n);
-                    s.sx = warp_sum_d(s.sx); s.sy = warp_sum_d(s.sy);
-                    s.sxx = warp_sum_d(s.sxx); s.syy = warp_sum_d(s.syy); s.sxy = warp_sum_d(s.sxy);
-                    if (G == 32) {
-                        if (lane == 0) { cval[cell] = ncc_from_sums(s); cflag[cell] |= kComputed; }
-                    } else {
-                        if (lane == 0) ctl.partd[gwarp] = s;
-                        gsync<G>();
-                        if (t == 0) {
-                            Sums q = ctl.partd[0];
-                            for (int w = 1; w < C::NWARPS; w++) {
-                                const Sums &z = ctl.partd[w];
-                                q.n += z.n; q.sx += z.sx; q.sy += z.sy; q.sxx += z.sxx; q.syy += z.syy; q.sxy += z.sxy;
-                            }
-                            cval[cell] = ncc_from_sums(q);
-                            cflag[cell] |= kComputed;
-                        }
-                        gsync<G>();
-                    }
+                    const int peak_du = pkx + OCW + 1 - dx2, peak_dv = pky + OCW + 1 - dy2;
+                    float du, dv;
+                    subpixel_fit(n9, peak_du, peak_dv, du, dv);
+                    a.dp[3 * (size_t)g] = a.negate * du;
+                    a.dp[3 * (size_t)g + 1] = a.negate * dv;
+                    a.dp[3 * (size_t)g + 2] = best;
+                    if (a.peak) a.peak[g] = make_int2(peak_du, peak_dv);
+                    if (a.ncell) a.ncell[g] = ncells;
                 }
-                if (G == 32) __syncwarp();
+                PROF_T(t_r1);
+                PROF_ADD(9, t_r1 - t_r0);
+                PROF_ADD(2, t_r1 - t_p0);
+            }
+            break;
+        }
+        // ---- requests: the unknown cells of the blocked pivots' probes form the round (<= MAXJ cells; a cell
+        //      that does not get in stays unlisted and its pivot asks again) --------------------------------------
+        for (int idx = t; idx < nblk * 9; idx += G) {
+            const int j = idx / 9, k = idx - 9 * j;
+            const int pos = ctl.blk[j];
+            const int cell = pos + (k % 3 - 1) * cw + (k / 3 - 1);
+            if (__float_as_uint(cval[cell]) != kUnknownBits) continue;
+            unsigned int *word = (unsigned int *)cflag + (cell >> 2);
+            const unsigned int bit = (unsigned int)kListed << (8 * (cell & 3));
+            if (atomicOr(word, bit) & bit) continue;             // listed by another pivot
+            const int slot = atomicAdd(&ctl.m, 1);
+            if (slot < C::MAXJ) {
+                const int cy = cell / cw;
+                ctl.job[slot] = (cy << 16) | (cell - cy * cw);
+            } else {
+                atomicAnd(word, ~bit);
             }
         }
+        PROF_T(t_p1);
+        PROF_ADD(8, t_p1 - t_w1);
+        PROF_ADD(2, t_p1 - t_p0);
+        gsync<G>();
+        const int m = min(ctl.m, C::MAXJ);
+        PROF_ADD(5, 1);
 
-        // ---- sub-pixel fit and output (:757-788) ------------------------------------------------------
-        if (t == 0) {
-            const int g = ctl.geo.g, dx2 = ctl.geo.dx2, dy2 = ctl.geo.dy2, cw = ctl.geo.cw, ch = ctl.geo.ch;
-            const int peak_x = ctl.st.peak_x, peak_y = ctl.st.peak_y, ncells = ctl.st.ncells;
-            const float best = ctl.st.best;
-            const float *cval = sa + ctl.geo.sa_elems;
-            const unsigned char *cflag = (const unsigned char *)(cval + ctl.geo.cell_elems);
-            float n9[9];
-            for (int rr = 0; rr < 3; rr++)
-                for (int cc = 0; cc < 3; cc++) {
-                    const int cx = peak_x - 1 + cc - (OCW + 1), cy = peak_y - 1 + rr - (OCW + 1);
-                    float v = -2.0f;   // never evaluated (or outside the evaluable region)
-                    if (cx >= 0 && cx < cw && cy >= 0 && cy < ch) {
-                        const int cell = cy * cw + cx;
-                        if (cflag[cell] & kVisible) v = cval[cell];
-                    }
-                    n9[rr * 3 + cc] = v;
-                }
-            float du, dv;
-            subpixel_fit(n9, peak_x - dx2, peak_y - dy2, du, dv);
-            a.dp[3 * (size_t)g] = a.negate * du;
-            a.dp[3 * (size_t)g + 1] = a.negate * dv;
-            a.dp[3 * (size_t)g + 2] = best;
-            if (a.peak) a.peak[g] = make_int2(peak_x - dx2, peak_y - dy2);
-            if (a.ncell) a.ncell[g] = ncells;
+        // ---- fast round: sum(fl(r*s)) for m cells, exact in FP32 ------------------------------------------
+        // Thread c < m owns cell c: its SAT corner loads are issued first so that their latency hides behind
+        // the loop.  sum(fl(s*s)), packed (sum(s) << 24 | nulls), flags = inside | (tx + 2*ty) << 1 where tx/ty
+        // say that the window reaches the never-written last column / row of the search area
+        unsigned long long w_ss = 0, w_pk = 1;
+        int w_flag = 0;
+        if (t < m) {
+            const int su0 = ctl.geo.su0, sv0 = ctl.geo.sv0, dx2 = ctl.geo.dx2, dy2 = ctl.geo.dy2, Dx2 = ctl.geo.Dx2, Dy2 = ctl.geo.Dy2;
+            const int job = ctl.job[t];
+            const int x0 = job_cx(job) + 1, y0 = job_cy(job) + 1;                     // window origin in the search area
+            const int ix0 = su0 - dx2 + x0, iy0 = sv0 - dy2 + y0;     // ... and in the image
+            // The last column / row of the search area is never written by the reference (H1): those pixels are
+            // nulls, i.e. the joint mask simply drops the chip's last column / row.  The FP32 loop already sees
+            // zeros there; only the SAT rectangles and n shrink.
+            const int tx = (x0 + S - 1 == Dx2 - 1), ty = (y0 + S - 1 == Dy2 - 1);
+            const bool inside = ix0 >= 0 && iy0 >= 0 && ix0 + S - tx <= a.W && iy0 + S - ty <= a.H;
+            w_flag = (inside ? 1 : 0) | ((tx + 2 * ty) << 1);
+            if (inside) rect_query_packed(a.sat_srch, W1, ix0, iy0, ix0 + S - tx, iy0 + S - ty, w_ss, w_pk);
         }
+        for (int c = 0; c < m; c++) {
+            const int job = ctl.job[c];
+            const int cy = job_cy(job), cx = job_cx(job);
+            unsigned int hi = 0;
+            int lo = 0;
+#pragma unroll
+            for (int rb = 0; rb < C::RB; rb++) {
+                // threads without chip pixels (r = col0 = 0, chip all zero) run the same code: no branch; a
+                // thread whose second row does not exist reads its first row again (times zero)
+                const float *sp = sa_thread + (cy + 1) * pitch + (cx + 1) + (rb ? row2 : 0);
+                // Two pixels per instruction (FMUL2 / FADD2 / FFMA2, sm_100): lane 0 of the packed pair
+                // accumulates the even pixels, lane 1 the odd ones -- the same two accumulators as a
+                // scalar loop would keep, at half the issue slots.  One accumulator pair per chip row
+                // (<= 16 pixels per accumulator).
+                f32x2 acc = pack2(a.A0, a.A0), lo2 = pack2(a.Mlo, a.Mlo);
+#pragma unroll
+                for (int k = 0; k < L; k += 2) {
+                    // an odd L ends with a (pixel, 0) pair: the zero is a literal, not a load
+                    const f32x2 rv = pack2(chip[rb][k], k + 1 < L ? chip[rb][k + 1] : 0.0f);
+                    const f32x2 sv = pack2(sp[k], k + 1 < L ? sp[k + 1] : 0.0f);
+                    if (EXACTP) {
+                        // every product is exact in FP32 (scaled operands < 2^12): fma(r, s, acc) ==
+                        // fadd(acc, fmul(r, s)) and fma(r, s, -z) == p - z, one instruction less per pixel
+                        const f32x2 s1 = fma2(rv, sv, acc);
+                        const f32x2 nz = sub2(acc, s1);
+                        lo2 = add2(lo2, fma2(rv, sv, nz));
+                        acc = s1;
+                    } else {
+                        const f32x2 pr = mul2(rv, sv);
+                        const f32x2 s1 = add2(acc, pr);
+                        const f32x2 z = sub2(s1, acc);
+                        lo2 = add2(lo2, sub2(pr, z));
+                        acc = s1;
+                    }
+                }
+                float acc0, acc1, lo0, lo1;
+                unpack2(acc, acc0, acc1);
+                unpack2(lo2, lo0, lo1);
+                hi += (__float_as_uint(acc0) - a.A0_bits) + (__float_as_uint(acc1) - a.A0_bits);
+                lo += (int)(__float_as_uint(lo0) - a.Mlo_bits) + (int)(__float_as_uint(lo1) - a.Mlo_bits);
+            }
+            hi = __reduce_add_sync(0xffffffffu, hi);
+            lo = __reduce_add_sync(0xffffffffu, lo);
+            if (lane == 0) ctl.part[gwarp][c] = make_int2((int)hi, lo);
+        }
+        gsync<G>();
+        PROF_T(t_c1);
+        PROF_ADD(3, t_c1 - t_p1);
+        // ---- finalize: thread c normalises cell c -------------------------------------------------------------
+        if (t < m) {
+            const int job = ctl.job[t];
+            const int cell = job_cy(job) * cw + job_cx(job);
+            const int trim = w_flag >> 1;
+            // bounding box of the round's cells: the probe-table update only looks there
+            atomicMin(&ctl.bbox[0], job_cx(job)); atomicMax(&ctl.bbox[1], job_cx(job));
+            atomicMin(&ctl.bbox[2], job_cy(job)); atomicMax(&ctl.bbox[3], job_cy(job));
+            if (ctl.chip_fast && (w_flag & 1) && (w_pk & 0xffffffull) == 0) {
+                long long hs = 0, ls = 0;
+#pragma unroll
+                for (int w = 0; w < C::NWARPS; w++) {
+                    const int2 q = ctl.part[w][t];
+                    hs += (unsigned int)q.x; ls += q.y;
+                }
+                Sums s;
+                s.n = (S - (trim & 1)) * (S - (trim >> 1));
+                s.sxy = (double)hs * a.hi_unit + (double)ls * a.lo_unit;
+                s.sx = (double)ctl.chip_s[trim] * a.inv_ref; s.sxx = (double)ctl.chip_ss[trim] * a.inv_ref2;
+                s.sy = (double)(w_pk >> 24) * a.inv_srch; s.syy = (double)w_ss * a.inv_srch2;
+                cval[cell] = ncc_from_sums(s);
+            } else {
+                // the window or the chip holds null pixels (no-data, zero-filled image border): masked evaluation
+                ctl.slowjob[atomicAdd(&ctl.nslow, 1)] = job;
+            }
+        }
+        gsync<G>();
+        // ---- masked round: the reference's 5-sum loop with null exclusion (:719-733), FP64 ------------------------
+        const int nslow = ctl.nslow;
+        if (nslow > 0) {
+            for (int c = 0; c < nslow; c++) {
+                const int job = ctl.slowjob[c];
+                const int cy = job_cy(job), cx = job_cx(job);
+                const int cell = cy * cw + cx;
+                Sums s = {0.0, 0.0, 0.0, 0.0, 0.0, 0};
+#pragma unroll
+                for (int rb = 0; rb < C::RB; rb++) {
+                    if (!active) break;
+                    const float *sp = sa_thread + (cy + 1) * pitch + (cx + 1) + (rb ? row2 : 0);
+#pragma unroll
+                    for (int k = 0; k < L; k++) {
+                        const float rv = chip[rb][k], sv = sp[k];
+                        if (rv >= a.min_dn && sv >= a.min_dn) {   // null exclusion, :723
+                            s.n++;
+                            s.sx += (double)rv; s.sy += (double)sv;
+                            s.sxx += (double)__fmul_rn(rv, rv);
+                            s.syy += (double)__fmul_rn(sv, sv);
+                            s.sxy += (double)__fmul_rn(rv, sv);
+                        }
+                    }
+                }
+                s.n = __reduce_add_sync(0xffffffffu, s.n);
+                s.sx = warp_sum_d(s.sx); s.sy = warp_sum_d(s.sy);
+                s.sxx = warp_sum_d(s.sxx); s.syy = warp_sum_d(s.syy); s.sxy = warp_sum_d(s.sxy);
+                if (G == 32) {
+                    if (lane == 0) cval[cell] = ncc_from_sums(s);
+                } else {
+                    if (lane == 0) ctl.partd[gwarp] = s;
+                    gsync<G>();
+                    if (t == 0) {
+                        Sums q = ctl.partd[0];
+                        for (int w = 1; w < C::NWARPS; w++) {
+                            const Sums &z = ctl.partd[w];
+                            q.n += z.n; q.sx += z.sx; q.sy += z.sy; q.sxx += z.sxx; q.syy += z.syy; q.sxy += z.sxy;
+                        }
+                        cval[cell] = ncc_from_sums(q);
+                    }
+                    gsync<G>();
+                }
+            }
+            if (t == 0) ctl.nslow = 0;   // next written after two more group barriers
+            gsync<G>();
+        }
+        // ---- probe table: positions whose nine cells are all known now ---------------------------------------
+        PROF_T(t_t0);
+        PROF_ADD(4, t_t0 - t_c1);
+        {
+            const int bx0 = max(ctl.bbox[0] - 1, 1), bx1 = min(ctl.bbox[1] + 1, cw - 2);
+            const int by0 = max(ctl.bbox[2] - 1, 1), by1 = min(ctl.bbox[3] + 1, ch - 2);
+            const int bw = bx1 - bx0 + 1, bh = by1 - by0 + 1;
+            const int total = (bw > 0 && bh > 0) ? bw * bh : 0;
+            for (int idx = t; idx < total; idx += G) {
+                const int yy = idx / bw;
+                const int pos = (by0 + yy) * cw + bx0 + (idx - yy * bw);
+                if (ctab[pos] & kTabComplete) continue;
+                float top = -CUDART_INF_F;
+                int kb = 4;
+                bool complete = true;
+#pragma unroll
+                for (int k = 0; k < 9; k++) {
+                    const float v = cval[pos + (k % 3 - 1) * cw + (k / 3 - 1)];
+                    complete = complete && __float_as_uint(v) != kUnknownBits;
+                    if (v > top) { top = v; kb = k; }
+                }
+                if (complete) ctab[pos] = (unsigned char)(kTabComplete | kb);
+            }
+            if (t == 0) { ctl.m = 0; ctl.nblk = 0; }   // every thread has read both (two barriers ago)
+        }
+        PROF_T(t_f1);
+        PROF_ADD(10, t_f1 - t_t0);
+        gsync<G>();
     }
 }
 
@@ -644,14 +592,17 @@ __global__ void __launch_bounds__(Cfg<OCW, G>::CTA, MINCTA) match2_kernel(const 
     using C = Cfg<OCW, G>;
     constexpr int S = C::S, L = C::L;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ Ctl<C::NWARPS, C::MAXJ> ctl_all[C::NGROUPS];
+    __shared__ Ctl<C::NWARPS, C::MAXJ, C::PMAX> ctl_all[C::NGROUPS];
 
     const int tid = threadIdx.x;
     const int grp = tid / G, t = tid - grp * G;
     const int lane = tid & 31, gwarp = t >> 5;
-    Ctl<C::NWARPS, C::MAXJ> &ctl = ctl_all[grp];
+    Ctl<C::NWARPS, C::MAXJ, C::PMAX> &ctl = ctl_all[grp];
+    // CTAs that share an SM (blockIdx.x = sm + j * num_sms in the first wave) run their serial sections in
+    // warps of different SM sub-partitions
+    const int lead = (int)((blockIdx.x / (unsigned)a.num_sms + grp) % C::NWARPS);
 
-    // dynamic shared memory, per group and per node: sa[Dy2*pitch] floats | cval[cells] floats | cflag[cells] bytes
+    // dynamic shared memory, per group and per node: sa[Dy2*pitch] floats | cval[cells] floats | cflag[cells] | ctab[cells] bytes
     float *sa = (float *)(smem_raw + (size_t)grp * a.grp_bytes);
 
     // this thread's chip slice: row r, columns [col0, col0+len)
@@ -661,7 +612,7 @@ __global__ void __launch_bounds__(Cfg<OCW, G>::CTA, MINCTA) match2_kernel(const 
     const int len = active ? min(L, S - col0) : 0;
     const int W1 = a.W + 1;
 
-    if (t == 0) ctl.node[0] = atomicAdd(a.counter, 1u);
+    if (t == 0) { ctl.node[0] = atomicAdd(a.counter, 1u); ctl.nslow = 0; }
     for (int iter = 0;; iter++) {
         gsync<G>();
         const unsigned int idx = ctl.node[iter & 1];
@@ -689,7 +640,7 @@ __global__ void __launch_bounds__(Cfg<OCW, G>::CTA, MINCTA) match2_kernel(const 
         const int cw = Dx2 - 2 * OCW - 1, ch = Dy2 - 2 * OCW - 1;   // cells whose 3x3 probe can be requested
         const int pitch = (Dx2 + 3) | 1;
         const int sa_elems = (Dy2 * pitch + 3) & ~3, cell_elems = (cw * ch + 15) & ~15;
-        if (sa_elems * 4 + cell_elems * 5 > a.grp_bytes) {
+        if (sa_elems * 4 + cell_elems * 6 > a.grp_bytes || P > C::PMAX) {
             if (t == 0) a.overflow_list[atomicAdd(a.overflow_count, 1u)] = g;
             continue;
         }
@@ -715,7 +666,12 @@ __global__ void __launch_bounds__(Cfg<OCW, G>::CTA, MINCTA) match2_kernel(const 
             rect_query(a.sat_srch, W1, x0, y0, x1, y1, q_ss, q_s, q_nul);
             q_area = max(x1 - x0, 0) * max(y1 - y0, 0); q_full = Dx2 * Dy2;
         }
-        for (int i = t; i < min(P, kPivCache); i += G) ctl.pivc[i] = piv[i];
+        // every pivot starts its climb at its own cell (:693-694); cell (cx, cy) <-> search-area position (cx+OCW+1, cy+OCW+1)
+        for (int i = t; i < P; i += G) {
+            const int2 pv = piv[i];
+            const int st = (a.sign * pv.x + dx2 - OCW - 1) | ((a.sign * pv.y + dy2 - OCW - 1) << 15);
+            ctl.wstart[i] = st; ctl.wpos[i] = st; ctl.wmax[i] = -2.0f;
+        }
 
         // ---- stage the chip through shared memory into registers (extract_refchip :845-855) ----
         if (u0 - OCW >= 0 && v0 - OCW >= 0 && u0 + OCW < a.W && v0 + OCW < a.H) {
@@ -773,18 +729,19 @@ __global__ void __launch_bounds__(Cfg<OCW, G>::CTA, MINCTA) match2_kernel(const 
                 }
             }
         }
-        for (int i = t; i < cw * ch; i += G) cflag[i] = 0;
-        if (t == 0) {   // written BEFORE the barrier: the other lanes of warp 0 read both right after it
-            ctl.geo = {g, P, su0, sv0, dx2, dy2, Dx2, Dy2, cw, ch, sa_elems, cell_elems, piv};
-            // phase 0: up-front first probes, 2: second probes, 1: the climb; nslow: masked-path cells pending in ctl.job[0..nslow)
-            ctl.st = {0, 0, 0, 0, 0, -1, -1, 1, dx2, dy2, 0, 0, 0, -2.0f, -2.0f};
+        // nothing known, nothing visible, no probe complete (cflag and ctab are adjacent: one sweep of words)
+        for (int i = t; i < cw * ch; i += G) cval[i] = __uint_as_float(kUnknownBits);
+        for (int i = t; i < cell_elems / 2; i += G) ((unsigned int *)cflag)[i] = 0u;
+        if (t == 0) {   // written BEFORE the barrier: the leader warp reads it right after
+            ctl.geo = {g, P, su0, sv0, dx2, dy2, Dx2, Dy2, cw, ch, sa_elems, cell_elems};
+            ctl.m = 0; ctl.nblk = 0;
         }
         gsync<G>();
         PROF_T(t_stage1);
         PROF_ADD(1, t_stage1 - t_node0);
         // this thread's view of the tile: row r, first column col0 (threads without chip pixels: the origin)
         node_rounds<OCW, G, EXACTP>(a, ctl, sa, sa + (active ? r * pitch + col0 : 0), chip, pitch,
-                                    (C::RB > 1 && active && r + C::RPT < S) ? C::RPT * pitch : 0, active, t, lane, gwarp);
+                                    (C::RB > 1 && active && r + C::RPT < S) ? C::RPT * pitch : 0, active, t, lane, gwarp, lead);
         PROF_T(t_node1);
         PROF_ADD(0, t_node1 - t_node0);
         PROF_ADD(6, 1);
@@ -815,7 +772,7 @@ int launch_one(mimc3cu_ctx *ctx, Match2Args &a, int groups_per_cta, size_t smem,
     return 0;
 }
 
-inline int group_size(int ocw) { return ocw >= 30 ? 256 : 32; }
+inline int pivot_max(int G) { return G == 32 ? 64 : 128; }   // Cfg::PMAX
 
 // Shared-memory bins of a launch: bin k runs `groups` node groups per CTA and is sized so that
 // `ctas` CTAs fit on an SM.  A node goes to the first bin it fits; the warp-per-node kernels get
@@ -835,6 +792,20 @@ inline int bin_table(int ocw, BinCfg *t) {
     t[0] = {32, 8, ocw == 7 ? 4 : 2}; t[1] = {32, 8, 2}; t[2] = {32, 8, 1}; t[3] = {256, 1, 3}; t[4] = {256, 1, 1};
     return 5;
 }
+// Development aid: MIMC3CU_BINS="40:128,1,5;30:64,4,2" replaces the FIRST bin of the named chip half-widths
+// (only combinations with a compiled instantiation: see the dispatch in launch_match2).
+inline int bin_table_env(int ocw, BinCfg *t) {
+    const int nb = bin_table(ocw, t);
+    if (const char *e = getenv("MIMC3CU_BINS")) {
+        for (const char *p = e; p && *p;) {
+            int o = 0, G = 0, groups = 0, ctas = 0;
+            if (sscanf(p, "%d:%d,%d,%d", &o, &G, &groups, &ctas) == 4 && o == ocw) t[0] = {G, groups, ctas};
+            p = strchr(p, ';');
+            if (p) p++;
+        }
+    }
+    return nb;
+}
 
 }  // namespace
 
@@ -849,21 +820,29 @@ bool match2_supported(const MatchLaunch &L, const Image *ref, const Image *srch)
     return b + ref->frac_bits + srch->frac_bits <= 37;
 }
 
-static size_t static_smem_bytes(int ocw, int G) {
+template <int OCW, int G>
+static size_t static_smem_of() {
     cudaFuncAttributes fa;
-    cudaError_t e = cudaErrorInvalidValue;
-    switch (ocw) {
-        case 7: e = G == 256 ? cudaFuncGetAttributes(&fa, match2_kernel<7, 256, false>) : cudaFuncGetAttributes(&fa, match2_kernel<7, 32, false>); break;
-        case 15: e = G == 256 ? cudaFuncGetAttributes(&fa, match2_kernel<15, 256, false>) : cudaFuncGetAttributes(&fa, match2_kernel<15, 32, false>); break;
-        case 30: e = G == 256 ? cudaFuncGetAttributes(&fa, match2_kernel<30, 256, false>) : cudaFuncGetAttributes(&fa, match2_kernel<30, 128, false>); break;
-        case 40: e = G == 256 ? cudaFuncGetAttributes(&fa, match2_kernel<40, 256, false>) : cudaFuncGetAttributes(&fa, match2_kernel<40, 128, false>); break;
+    return cudaFuncGetAttributes(&fa, match2_kernel<OCW, G, false>) == cudaSuccess ? fa.sharedSizeBytes : 16384;
+}
+static size_t static_smem_bytes(int ocw, int G) {
+    switch (ocw * 1000 + G) {
+        case 7032: return static_smem_of<7, 32>();
+        case 7256: return static_smem_of<7, 256>();
+        case 15032: return static_smem_of<15, 32>();
+        case 15256: return static_smem_of<15, 256>();
+        case 30064: return static_smem_of<30, 64>();
+        case 30128: return static_smem_of<30, 128>();
+        case 30256: return static_smem_of<30, 256>();
+        case 40128: return static_smem_of<40, 128>();
+        case 40256: return static_smem_of<40, 256>();
     }
-    return e == cudaSuccess ? fa.sharedSizeBytes : 12288;
+    return 16384;
 }
 
-static void build_bins(mimc3cu_ctx *ctx, PivotSet *ps, PivotSet::Bins &B, int ocw) {
+static int build_bins(mimc3cu_ctx *ctx, PivotSet *ps, PivotSet::Bins &B, int ocw) {
     BinCfg tab[kMaxBins];
-    const int nb = bin_table(ocw, tab);
+    const int nb = bin_table_env(ocw, tab);
     const size_t usable = ctx->smem_optin;
     for (int k = 0; k < nb; k++) {
         const size_t fixed = static_smem_bytes(ocw, tab[k].G) + 256;         // static control blocks + slack
@@ -879,9 +858,10 @@ static void build_bins(mimc3cu_ctx *ctx, PivotSet *ps, PivotSet::Bins &B, int oc
         const int64_t Dx2 = 2 * (ps->last_u[g] + ocw + 2) + 1, Dy2 = 2 * (ps->last_v[g] + ocw + 2) + 1;
         const int64_t pitch = (Dx2 + 3) | 1, need_sa = (Dy2 * pitch + 3) & ~3LL;
         const int64_t need_cells = ((Dx2 - 2 * ocw - 1) * (Dy2 - 2 * ocw - 1) + 15) & ~15LL;
-        const int64_t need = need_sa * 4 + need_cells * 5;   // same formula as the kernel's fit test
+        const int64_t need = need_sa * 4 + need_cells * 6;   // same formula as the kernel's fit test
+        const int P = std::max(ps->last_u[g], ps->last_v[g]) + 1;   // get_uv_pivot steps by one pixel along the dominant axis
         int k = 0;
-        while (k < nb && need > B.grp_bytes[k]) k++;
+        while (k < nb && (need > B.grp_bytes[k] || P > pivot_max(tab[k].G))) k++;
         if (k == nb) k = kMaxBins;   // general kernel
         which[g] = (uint8_t)k; cnt[k]++;
     }
@@ -890,17 +870,19 @@ static void build_bins(mimc3cu_ctx *ctx, PivotSet *ps, PivotSet::Bins &B, int oc
     for (int k = 0, acc = 0; k <= kMaxBins; k++) { B.start[k] = acc; B.count[k] = (int32_t)cnt[k]; pos[k] = acc; acc += (int)cnt[k]; }
     for (int32_t g = 0; g < ps->n; g++) all[(size_t)pos[which[g]]++] = g;
     if ((size_t)ps->n > B.lists_cap) {
-        if (B.lists) cudaFree(B.lists);
-        cudaMalloc(&B.lists, sizeof(int32_t) * (size_t)ps->n);
+        if (B.lists) { CU_CHECK(ctx, cudaFree(B.lists)); B.lists = nullptr; B.lists_cap = 0; }
+        CU_CHECK(ctx, cudaMalloc(&B.lists, sizeof(int32_t) * (size_t)ps->n));
         B.lists_cap = (size_t)ps->n;
     }
-    cudaMemcpy(B.lists, all.data(), sizeof(int32_t) * all.size(), cudaMemcpyHostToDevice);
+    // ordered against the matcher launches on the context stream (upload_sync in api.cu explains why not cudaMemcpy)
+    if (int rc = upload_sync(ctx, B.lists, all.data(), sizeof(int32_t) * all.size())) return rc;
     B.ocw = ocw;
     if (getenv("MIMC3CU_DEBUG_BINS")) {
         fprintf(stderr, "[mimc3cu] ocw %d bins:", ocw);
         for (int k = 0; k < nb; k++) fprintf(stderr, " {G %d x %d, %d CTA/SM, %lld B/node}: %lld", tab[k].G, tab[k].groups, tab[k].ctas, (long long)B.grp_bytes[k], (long long)cnt[k]);
         fprintf(stderr, "  general kernel: %lld of %d nodes\n", (long long)cnt[kMaxBins], ps->n);
     }
+    return 0;
 }
 
 int launch_match2(mimc3cu_ctx *ctx, const MatchLaunch &L, const Image *ref, const Image *srch, PivotSet *ps) {
@@ -913,7 +895,7 @@ int launch_match2(mimc3cu_ctx *ctx, const MatchLaunch &L, const Image *ref, cons
         // no launch that reads this slot's node lists can be in flight: set_pivots waited for them, and a second
         // chip size on the same slot uses the other cache entry (a third one recycles: wait for the slot then)
         if (B->ocw >= 0 && ps->last_use) CU_CHECK(ctx, cudaEventSynchronize(ps->last_use));
-        build_bins(ctx, ps, *B, L.ocw);
+        if (int rc = build_bins(ctx, ps, *B, L.ocw)) return rc;
     }
     if (ctx->overflow_cap < (size_t)L.n) {
         CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -930,6 +912,7 @@ int launch_match2(mimc3cu_ctx *ctx, const MatchLaunch &L, const Image *ref, cons
     a.node_uv = L.node_uv; a.off_u = L.off_u; a.off_v = L.off_v; a.csr_off = L.csr_off; a.piv = (const int2 *)L.piv;
     a.sign = L.sign; a.negate = L.negate; a.dp = L.dp; a.peak = (int2 *)L.peak; a.ncell = L.ncell;
     a.min_dn = min_dn_float();
+    a.num_sms = std::max(1, ctx->num_sms);
     // accumulator biases: A0 = 2^(b+4) with 2^b >= max product; lo unit = product granularity
     const double maxprod = std::max(1.0, (double)ref->max_value * (double)srch->max_value);
     int b = 0;
@@ -951,7 +934,7 @@ int launch_match2(mimc3cu_ctx *ctx, const MatchLaunch &L, const Image *ref, cons
         CU_CHECK(ctx, cudaMemcpyAsync(ctx->counter + 8, &c3, sizeof(c3), cudaMemcpyHostToDevice, ctx->stream));
     }
     BinCfg tab[kMaxBins];
-    const int nb = bin_table(L.ocw, tab);
+    const int nb = bin_table_env(L.ocw, tab);
     // products of the scaled operands below 2^24 are exact in FP32: the FFMA form of the inner loop applies
     const bool exactp = b + ref->frac_bits + srch->frac_bits <= 24;
     for (int k = 0; k < nb; k++) {
@@ -973,10 +956,12 @@ int launch_match2(mimc3cu_ctx *ctx, const MatchLaunch &L, const Image *ref, cons
                 break;
             case 30:
                 if (tab[k].G == 256) rc = exactp ? launch_one<30, 256, true>(ctx, a, 1, smem, a.n_list, nullptr) : launch_one<30, 256, false>(ctx, a, 1, smem, a.n_list, nullptr);
+                else if (tab[k].G == 64) rc = exactp ? launch_one<30, 64, true>(ctx, a, tab[k].groups, smem, a.n_list, nullptr) : launch_one<30, 64, false>(ctx, a, tab[k].groups, smem, a.n_list, nullptr);
                 else rc = exactp ? launch_one<30, 128, true>(ctx, a, tab[k].groups, smem, a.n_list, nullptr) : launch_one<30, 128, false>(ctx, a, tab[k].groups, smem, a.n_list, nullptr);
                 break;
             case 40:
-                if (tab[k].G == 128) rc = exactp ? launch_one<40, 128, true>(ctx, a, 1, smem, a.n_list, nullptr) : launch_one<40, 128, false>(ctx, a, 1, smem, a.n_list, nullptr);
+                if (tab[k].G == 128 && tab[k].ctas >= 5) rc = exactp ? launch_one<40, 128, true, 5>(ctx, a, 1, smem, a.n_list, nullptr) : launch_one<40, 128, false, 5>(ctx, a, 1, smem, a.n_list, nullptr);
+                else if (tab[k].G == 128) rc = exactp ? launch_one<40, 128, true>(ctx, a, 1, smem, a.n_list, nullptr) : launch_one<40, 128, false>(ctx, a, 1, smem, a.n_list, nullptr);
                 else if (tab[k].ctas <= 2) rc = exactp ? launch_one<40, 256, true, 2>(ctx, a, 1, smem, a.n_list, nullptr) : launch_one<40, 256, false, 2>(ctx, a, 1, smem, a.n_list, nullptr);
                 else rc = exactp ? launch_one<40, 256, true>(ctx, a, 1, smem, a.n_list, nullptr) : launch_one<40, 256, false>(ctx, a, 1, smem, a.n_list, nullptr);
                 break;
@@ -986,13 +971,14 @@ int launch_match2(mimc3cu_ctx *ctx, const MatchLaunch &L, const Image *ref, cons
     }
 #ifdef MIMC3CU_PROFILE
     {
-        unsigned long long h[8];
+        unsigned long long h[16];
         cudaStreamSynchronize(ctx->stream);
         cudaMemcpyFromSymbol(h, g_prof, sizeof(h));
         if (h[6])
-            fprintf(stderr, "[prof ocw %d] nodes %llu rounds/node %.2f  cycles/node: total %.0f staging %.0f produce %.0f compute %.0f finalize %.0f\n",
-                    L.ocw, h[6], (double)h[5] / h[6], (double)h[0] / h[6], (double)h[1] / h[6], (double)h[2] / h[6], (double)h[3] / h[6],
-                    (double)h[4] / h[6]);
+            fprintf(stderr, "[prof ocw %d] nodes %llu rounds/node %.2f  cycles/node: total %.0f staging %.0f leader %.0f (walk %.0f requests %.0f replay %.0f) "
+                            "compute %.0f finalize %.0f table %.0f\n",
+                    L.ocw, h[6], (double)h[5] / h[6], (double)h[0] / h[6], (double)h[1] / h[6], (double)h[2] / h[6], (double)h[7] / h[6],
+                    (double)h[8] / h[6], (double)h[9] / h[6], (double)h[3] / h[6], (double)h[4] / h[6], (double)h[10] / h[6]);
         memset(h, 0, sizeof(h));
         cudaMemcpyToSymbol(g_prof, h, sizeof(h));
     }

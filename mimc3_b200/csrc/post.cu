@@ -519,12 +519,17 @@ int post_run_band(mimc3cu_ctx *ctx, const float *dp, const double *xyuvav, const
     if (dimx < 2 || gdimy < 1) return mimc3cu_fail(ctx, "postprocess: bad grid %dx%d", gdimy, dimx);
     if (own_row0 < 0 || own_rows < 1 || own_row0 + own_rows > gdimy) return mimc3cu_fail(ctx, "postprocess: bad band [%d,+%d) of %d rows", own_row0, own_rows, gdimy);
     const int halo = band_halo_rows(p);
-    if (comm && own_rows < halo && own_rows != gdimy)
+    // communication: the caller's callbacks (any transport), or the context's own NCCL communicator (comm.cu)
+    const bool nccl = !comm && ctx->comm && ctx->comm->world > 1;
+    const bool banded = comm || nccl;
+    if (banded && own_rows < halo && own_rows != gdimy)
         return mimc3cu_fail(ctx, "postprocess: a band needs at least %d node rows (has %d)", halo, own_rows);
     Band B;
     B.dimx = dimx; B.gdimy = gdimy;
-    const int ht = comm ? std::min(halo, own_row0) : 0, hb = comm ? std::min(halo, gdimy - own_row0 - own_rows) : 0;
-    if (!comm && own_rows != gdimy) return mimc3cu_fail(ctx, "postprocess: a partial band needs a communicator");
+    const int ht = banded ? std::min(halo, own_row0) : 0, hb = banded ? std::min(halo, gdimy - own_row0 - own_rows) : 0;
+    if (!banded && own_rows != gdimy) return mimc3cu_fail(ctx, "postprocess: a partial band needs a communicator");
+    if (nccl && ((ht != 0 && ht != halo) || (hb != 0 && hb != halo)))
+        return mimc3cu_fail(ctx, "postprocess: every band needs at least %d node rows", halo);
     B.grow0 = own_row0 - ht; B.rows = own_rows + ht + hb; B.own0 = ht; B.own1 = ht + own_rows;
     const int32_t nl = B.rows * dimx, n = own_rows * dimx, off = B.own0 * dimx;
     CU_CHECK(ctx, cudaSetDevice(ctx->device));
@@ -536,15 +541,20 @@ int post_run_band(mimc3cu_ctx *ctx, const float *dp, const double *xyuvav, const
     int32_t h_ctr[4];
 
     auto exchange = [&](std::initializer_list<void *> arrays, std::initializer_list<int32_t> bytes) -> int {
-        if (!comm || (ht == 0 && hb == 0 && own_rows == gdimy)) return 0;
-        CU_CHECK(ctx, cudaStreamSynchronize(st));
+        if (!banded || (ht == 0 && hb == 0 && own_rows == gdimy)) return 0;
         std::vector<void *> a(arrays); std::vector<int32_t> eb(bytes);
+        if (nccl) return bandcomm_halo_exchange(ctx, a.data(), eb.data(), (int32_t)a.size(), dimx, B.rows, B.own0, B.own1, halo);   // enqueued, no host wait
+        CU_CHECK(ctx, cudaStreamSynchronize(st));
         if (comm->halo_exchange(comm->user, a.data(), eb.data(), (int32_t)a.size())) return mimc3cu_fail(ctx, "postprocess: halo exchange failed");
         return 0;
     };
-    auto allreduce = [&](int32_t *vals, int32_t count) -> int {
-        if (!comm) return 0;
-        if (comm->allreduce_sum(comm->user, vals, count)) return mimc3cu_fail(ctx, "postprocess: all-reduce failed");
+    // sweep counters, summed over all bands, on the host: the one synchronisation per sweep
+    auto read_counters = [&](int32_t *host, int32_t count) -> int {
+        if (nccl)
+            if (int rc = bandcomm_allreduce_sum(ctx, P.ctr, count)) return rc;
+        CU_CHECK(ctx, cudaMemcpyAsync(host, P.ctr, count * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        CU_CHECK(ctx, cudaStreamSynchronize(st));
+        if (comm && comm->allreduce_sum(comm->user, host, count)) return mimc3cu_fail(ctx, "postprocess: all-reduce failed");
         return 0;
     };
 
@@ -562,9 +572,7 @@ int post_run_band(mimc3cu_ctx *ctx, const float *dp, const double *xyuvav, const
     dpf0_kernel<<<nb, kT, 0, st>>>(P.mvn + (size_t)off * K * 5, P.ncl + off, n, K, P.dpf0 + off, P.id + off, P.dx + off, P.dy + off,
                                    P.dxb + off, P.dyb + off, P.noi + off, P.ctr);
     ctx->launches += 2;
-    CU_CHECK(ctx, cudaMemcpyAsync(h_ctr, P.ctr, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CU_CHECK(ctx, cudaStreamSynchronize(st));
-    if (int rc = allreduce(h_ctr, 4)) return rc;
+    if (int rc = read_counters(h_ctr, 4)) return rc;
     const int32_t holes0 = h_ctr[2];
     if (int rc = exchange({P.dx, P.dy, P.noi}, {4, 4, 4})) return rc;
 
@@ -588,9 +596,7 @@ int post_run_band(mimc3cu_ctx *ctx, const float *dp, const double *xyuvav, const
                                                      thres_n, thres_weight, P.ctr);
                 dpf1_commit_kernel<<<nb, kT, 0, st>>>(P.dx + off, P.dy + off, P.dxb + off, P.dyb + off, P.ncl + off, n, P.ctr);
                 ctx->launches += 2;
-                CU_CHECK(ctx, cudaMemcpyAsync(h_ctr, P.ctr, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-                CU_CHECK(ctx, cudaStreamSynchronize(st));
-                if (int rc = allreduce(h_ctr, 2)) return rc;
+                if (int rc = read_counters(h_ctr, 2)) return rc;
                 processed = h_ctr[0];
                 unprocessed = h_ctr[1];
                 if (processed != 0)
@@ -630,16 +636,16 @@ int post_run_band(mimc3cu_ctx *ctx, const float *dp, const double *xyuvav, const
                                            nruv, B, P.ctr);
         ps_commit_kernel<<<nb, kT, 0, st>>>(P.dx + off, P.dy + off, P.id + off, P.dxb + off, P.dyb + off, P.bid + off, n);
         ctx->launches += 2;
-        if (comm && (ht || hb)) {   // dirty flags scattered into the neighbours' rows: OR them into their owners
+        if (nccl) {                   // dirty flags scattered into the neighbours' rows: OR them into their owners
+            if (int rc = bandcomm_halo_or_reduce(ctx, next, dimx, B.rows, B.own0, B.own1, halo)) return rc;
+        } else if (comm && (ht || hb)) {
             CU_CHECK(ctx, cudaStreamSynchronize(st));
             if (comm->halo_or_reduce(comm->user, next)) return mimc3cu_fail(ctx, "postprocess: halo OR-reduce failed");
         }
         ps_compare_kernel<<<nb, kT, 0, st>>>(P.stack + off, P.cap_n, next + off, nstack, n, P.ctr + 8, P.ctr + 1);
         ctx->launches++;
         int32_t h[128];
-        CU_CHECK(ctx, cudaMemcpyAsync(h, P.ctr, 128 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-        CU_CHECK(ctx, cudaStreamSynchronize(st));
-        if (int rc = allreduce(h, 128)) return rc;
+        if (int rc = read_counters(h, 128)) return rc;
         any = h[0] != 0;
         bool fluct = false;
         for (int k = nstack - 1; k >= 0; k--) if (h[8 + k] == 0) { fluct = true; break; }

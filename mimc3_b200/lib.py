@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmimc3cu.so")
+# MIMC3CU_LIB selects a development variant of the library (mimc3_b200/build.py --variant); there is still no fallback
+LIB_PATH = os.environ.get("MIMC3CU_LIB") or os.path.join(HERE, "libmimc3cu.so")
 
 
 class Mimc3CuError(RuntimeError):
@@ -68,6 +69,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "mimc3cu_match": (C.c_int, [vp, i32, i32, vp, i32, i32, i32, i32, vp, vp, vp]),
         "mimc3cu_find_ncc_peak_batch": (C.c_int, [vp, vp, i32, vp, i32, i32, vp, i32, vp, vp, vp]),
         "mimc3cu_multimatch_async": (C.c_int, [vp, i32, i32, i32, i32, vp, C.POINTER(Params), vp, vp]),
+        "mimc3cu_multimatch_diag_async": (C.c_int, [vp, i32, i32, i32, i32, vp, C.POINTER(Params), vp, vp, vp]),
         "mimc3cu_cluster_async": (C.c_int, [vp, vp, i32, i32, vp, vp]),
         "mimc3cu_postprocess": (C.c_int, [vp, vp, vp, C.POINTER(Params), vp, vp]),
         "mimc3cu_postprocess_stage": (C.c_int, [vp, i32, vp]),
@@ -83,6 +85,12 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
                                                C.POINTER(i32), C.POINTER(i32)]),
         "mimc3cu_band_halo": (C.c_int, [C.POINTER(Params)]),
         "mimc3cu_postprocess_band": (C.c_int, [vp, vp, vp, C.POINTER(Params), i32, i32, vp, vp, vp]),
+        "mimc3cu_comm_unique_id": (C.c_int, [vp]),
+        "mimc3cu_comm_init_rank": (C.c_int, [vp, vp, i32, i32]),
+        "mimc3cu_comm_init_all": (C.c_int, [C.POINTER(vp), i32]),
+        "mimc3cu_comm_destroy": (None, [vp]),
+        "mimc3cu_comm_info": (C.c_int, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64), C.POINTER(i64)]),
+        "mimc3cu_comm_gather": (C.c_int, [vp, vp, vp, vp, i32]),
         "mimc3cu_set_matcher": (C.c_int, [vp, i32]),
         "mimc3cu_last_matcher": (C.c_int, [vp]),
         "mimc3cu_image_class": (C.c_int, [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(f32)]),
@@ -107,6 +115,8 @@ EXPORTED_SYMBOLS = (
     "mimc3cu_timing_read", "mimc3cu_malloc", "mimc3cu_free", "mimc3cu_memcpy_d2h",
     "mimc3cu_memcpy_h2d", "mimc3cu_set_matcher", "mimc3cu_last_matcher", "mimc3cu_image_class",
     "mimc3cu_get_offset_image", "mimc3cu_band_halo", "mimc3cu_postprocess_band", "mimc3cu_image_fill_zero",
+    "mimc3cu_multimatch_diag_async", "mimc3cu_comm_unique_id", "mimc3cu_comm_init_rank", "mimc3cu_comm_init_all",
+    "mimc3cu_comm_destroy", "mimc3cu_comm_info", "mimc3cu_comm_gather",
 )
 
 
@@ -144,6 +154,15 @@ def params_for(xyuvav: np.ndarray, dimx: int, dimy: int, dt: float) -> Params:
 def band_halo(params) -> int:
     """Node rows of halo each band keeps of its neighbours (mimc3cu_band_halo)."""
     return int(load_library().mimc3cu_band_halo(C.byref(params)))
+
+
+def comm_unique_id() -> bytes:
+    """128-byte NCCL unique id (call on one rank, distribute to the others, then Context.comm_init_rank)."""
+    L = load_library()
+    buf = C.create_string_buffer(128)
+    if L.mimc3cu_comm_unique_id(C.cast(buf, C.c_void_p)):
+        raise Mimc3CuError(L.mimc3cu_last_error(None).decode())
+    return buf.raw
 
 
 def get_uv_pivot(xyuvav, dt, mpp, ocw, H, W, aw_sf=1.8, aw_cre=10.0):
@@ -291,10 +310,10 @@ class Context:
                                                     p.shape[0], _ptr(uv), _ptr(pk), _ptr(nc)))
         return uv, pk, nc
 
-    def multimatch_async(self, i0, i1, i0c, i1c, offset, params, dp_dev, ncell_dev=None):
+    def multimatch_async(self, i0, i1, i0c, i1c, offset, params, dp_dev, ncell_dev=None, peak_dev=None):
         off = np.ascontiguousarray(offset, dtype=np.int32)
-        self._ck(self.L.mimc3cu_multimatch_async(self.h, i0, i1, i0c, i1c, _ptr(off), C.byref(params), _ptr(dp_dev),
-                                                 _ptr(ncell_dev)))
+        self._ck(self.L.mimc3cu_multimatch_diag_async(self.h, i0, i1, i0c, i1c, _ptr(off), C.byref(params), _ptr(dp_dev),
+                                                      _ptr(ncell_dev), _ptr(peak_dev)))
 
     # control points ---------------------------------------------------------------------------------
     def get_offset_image(self, i0, i1, xyuvav, params, seed):
@@ -318,7 +337,8 @@ class Context:
 
     def postprocess_band(self, dp_dev, xyuvav_global, params_global, own_row0, own_rows, comm, planes_dev):
         """One band of node rows of mimc2_postprocess (collective over the bands).  ``comm`` is a
-        bands.BandComm (or None for the single band [0, dimy))."""
+        bands.BandComm, or None: the single band [0, dimy), or -- with comm_init_rank done -- the library's
+        own NCCL communicator."""
         x = np.ascontiguousarray(xyuvav_global, dtype=np.float64)
         stats = np.zeros(4, np.int32)
         cptr = C.cast(C.pointer(comm.struct), C.c_void_p) if comm is not None else None
@@ -328,6 +348,22 @@ class Context:
             raise comm.error
         self._ck(rc)
         return stats
+
+    # the library's own NCCL band communicator ------------------------------------------------------------------
+    def comm_init_rank(self, unique_id: bytes, rank: int, world: int):
+        """Attach an NCCL communicator (one rank per node-row band); ``unique_id`` = comm_unique_id() of rank 0."""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._ck(self.L.mimc3cu_comm_init_rank(self.h, C.cast(buf, C.c_void_p), rank, world))
+
+    def comm_info(self):
+        r = C.c_int32(); w = C.c_int32(); e = C.c_int64(); a = C.c_int64()
+        if self.L.mimc3cu_comm_info(self.h, C.byref(r), C.byref(w), C.byref(e), C.byref(a)):
+            return None
+        return {"rank": r.value, "world": w.value, "halo_exchanges": e.value, "allreduces": a.value}
+
+    def comm_gather(self, send_dev, bytes_per_rank, recv_dev, root=0):
+        b = np.ascontiguousarray(bytes_per_rank, dtype=np.int64)
+        self._ck(self.L.mimc3cu_comm_gather(self.h, _ptr(send_dev), _ptr(b), _ptr(recv_dev), root))
 
     def postprocess_stage(self, which, n):
         out = np.empty(n, np.float32 if which in (2, 3, 5, 6) else np.int32)

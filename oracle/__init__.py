@@ -85,6 +85,9 @@ class Oracle:
         L.orc_match.restype = None
         L.orc_match.argtypes = [_f32p, _f32p, C.c_int32, C.c_int32, _f64p, C.c_int32, _i32p, _i32p, _i32p,
                                 C.c_int32, C.c_int32, _f32p, _i32p, _i32p]
+        L.orc_model_match.restype = None
+        L.orc_model_match.argtypes = [_f32p, _f32p, C.c_int32, C.c_int32, _f64p, C.c_int32, _i32p, _i32p, _i32p,
+                                      C.c_int32, C.c_int32, C.c_int32, _f32p, _i32p, _i32p, _i32p]
         L.orc_find_ncc_peak.restype = None
         L.orc_find_ncc_peak.argtypes = [_f32p, C.c_int32, _f32p, C.c_int32, C.c_int32, _i32p, C.c_int32,
                                         _f32p, _i32p, _i32p]
@@ -135,6 +138,21 @@ class Oracle:
         self.lib.orc_match(i0, i1, H, W, x, n, _as(offset, np.int32), _as(csr_off, np.int32), piv,
                            sign, ocw, out, peak, ncell)
         return out, peak, ncell
+
+    def model_match(self, i0, i1, xyuvav, offset, csr_off, piv, sign, ocw, maxj=64):
+        """orc_match through the CUDA kernel's explore/replay schedule (leader_model.c) -> (dp, peak, ncell,
+        stats (n,4): rounds, cells computed, explore steps, replay steps)."""
+        i0 = _as(i0, np.float32); i1 = _as(i1, np.float32); x = _as(xyuvav, np.float64)
+        H, W = i0.shape
+        n = x.shape[0]
+        out = np.zeros((n, 3), np.float32); peak = np.zeros((n, 2), np.int32); ncell = np.zeros(n, np.int32)
+        stats = np.zeros((n, 4), np.int32)
+        piv = _as(piv, np.int32).reshape(-1, 2)
+        if piv.shape[0] == 0:
+            piv = np.zeros((1, 2), np.int32)
+        self.lib.orc_model_match(i0, i1, H, W, x, n, _as(offset, np.int32), _as(csr_off, np.int32), piv,
+                                 sign, ocw, maxj, out, peak, ncell, stats)
+        return out, peak, ncell, stats
 
     def find_ncc_peak(self, refchip, sarea, piv):
         r = _as(refchip, np.float32); s = _as(sarea, np.float32); p = _as(piv, np.int32).reshape(-1, 2)
@@ -235,6 +253,9 @@ class Reference:
         L.ref_quiet.restype = None
         L.ref_quiet.argtypes = [C.c_int]
         L.ref_num_threads.restype = C.c_int
+        if hasattr(L, "ref_set_num_threads"):
+            L.ref_set_num_threads.restype = None
+            L.ref_set_num_threads.argtypes = [C.c_int]
         self.quiet = quiet
 
     def _q(self, on):
@@ -243,6 +264,12 @@ class Reference:
 
     def num_threads(self) -> int:
         return int(self.lib.ref_num_threads())
+
+    def set_num_threads(self, n: int) -> int:
+        """OpenMP team size of the reference's parallel regions (returns what is in effect)."""
+        if hasattr(self.lib, "ref_set_num_threads"):
+            self.lib.ref_set_num_threads(int(n))
+        return self.num_threads()
 
     def set_globals(self, xyuvav, dimx, dimy, dt, num_dp=32):
         x = np.asarray(xyuvav)

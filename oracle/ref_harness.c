@@ -230,6 +230,8 @@ int ref_get_offset_image(float *i0, float *i1, int32_t H, int32_t W, double *xyu
 }
 
 int ref_num_threads(void) { return omp_get_max_threads(); }
+/* torchrun exports OMP_NUM_THREADS=1 to its workers: bench.py's reference arm sets the team size explicitly */
+void ref_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
 /* The reference prints progress and debug matrices to stdout (e.g. the node (15,30)
  * dump inside get_dpf1, MIMC_module.c:1501-1544).  Tests silence it. */

@@ -132,3 +132,30 @@ def test_control_point_stage_equals_reference(orc, ref, seed_time):
     assert rc == rc_r == 1
     assert np.array_equal(off, off_r) and np.array_equal(off, np.array(sc.offset, np.int32))
     assert np.array_equal(flag, flag_r) and flag.sum() > 0
+
+
+@pytest.mark.parametrize("maxj", (32, 64))
+@pytest.mark.parametrize("case", ("wedge", "fast"))
+def test_explore_replay_schedule_equals_reference_algorithm(orc, case, maxj):
+    """The CUDA matcher evaluates cells in "explore" rounds and then replays the reference's state machine
+    (csrc/match2.cu); oracle/leader_model.c restates that schedule on the CPU.  It must give the oracle's
+    results bit for bit -- peaks, evaluated-cell counts, dp -- and never leave a needed cell unevaluated."""
+    from mimc3_b200 import synth
+    if case == "wedge":
+        sc = synth.make_scene(H=448, W=448, dtype="u8", spacing=29, seed=5, peak_px=6.3, null_wedge=True)
+    else:
+        sc = synth.make_scene(H=512, W=512, dtype="u16", spacing=53, seed=3, peak_px=30.0, apriori_gain=0.9,
+                              band_width_frac=0.2, decorrelated_patches=4)
+    i0, i1 = sc.i0.numpy(), sc.i1.numpy()
+    H, W = i0.shape
+    mpp = float(np.float32((sc.xyuvav[1, 0] - sc.xyuvav[0, 0]) / (sc.xyuvav[1, 2] - sc.xyuvav[0, 2])))
+    offset = np.array(sc.offset, np.int32)
+    for ocw in (7, 30):
+        off, piv = orc.get_uv_pivot(sc.xyuvav, sc.dt, mpp, ocw, H, W)
+        for sign, a, b, o in ((1, i0, i1, offset), (-1, i1, i0, -offset)):
+            dp, pk, nc = orc.match(a, b, sc.xyuvav, o, off, piv, sign, ocw)
+            dm, pm, nm, st = orc.model_match(a, b, sc.xyuvav, o, off, piv, sign, ocw, maxj)
+            assert (st[:, 0] >= 0).all(), "the schedule left a cell the replay needs unevaluated"
+            assert np.array_equal(pk, pm) and np.array_equal(nc, nm)
+            assert np.array_equal(np.isnan(dp), np.isnan(dm)) and np.array_equal(dp[~np.isnan(dp)], dm[~np.isnan(dm)])
+            assert st[:, 1].sum() <= 1.02 * nc.sum() + 9 * len(nc)      # explore evaluates (almost) only what the reference does
