@@ -70,6 +70,10 @@ void GMA_float_conv2(GMA_float *in, GMA_float *kernel, GMA_float *out);
 
 /* Optional: release device memory before exit (also registered with atexit). */
 void mimc3_dropin_shutdown(void);
+/* Device copies of images, nodes and results are keyed by the HOST payload pointer (img->data, xyuvav->data).  A
+ * driver that rewrites such a buffer in place, or frees it and gets the same address back for other content, must
+ * call this before the next module call (get_offset_image does it for everything: it opens a new image pair). */
+void mimc3_dropin_invalidate(const void *host_payload);
 
 #ifdef __cplusplus
 }

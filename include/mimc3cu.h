@@ -241,6 +241,9 @@ int mimc3cu_comm_gather(mimc3cu_ctx *ctx, const void *send, const int64_t *bytes
  * (n = the owned nodes of the band in band mode). */
 int mimc3cu_postprocess_stage(mimc3cu_ctx *ctx, int32_t which, void *host);
 
+/* du, dv -> -du, -dv on a device (n, 3) result: what main does to the swapped passes on the host (MIMC_main.c:289-293). */
+int mimc3cu_dp_negate_uv_async(mimc3cu_ctx *ctx, float *dp_dev, int32_t n);
+
 /* main()'s tail, MIMC_main.c:356-402: mean of the non-NaN du,dv removed (sequential
  * float sums), px -> m/yr, vy sign flip, sqrt of the variances. In place on planes_dev. */
 int mimc3cu_finalize(mimc3cu_ctx *ctx, float *planes_dev, const mimc3cu_params *p, float *du_cp, float *dv_cp);

@@ -204,7 +204,7 @@ void mimc3cu_destroy(mimc3cu_ctx *ctx) {
 
 const char *mimc3cu_last_error(const mimc3cu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_mimc3cu_error.c_str(); }
 void *mimc3cu_stream(mimc3cu_ctx *ctx) { return (void *)ctx->stream; }
-int mimc3cu_sync(mimc3cu_ctx *ctx) { CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); return 0; }
+int mimc3cu_sync(mimc3cu_ctx *ctx) { CU_CHECK(ctx, cudaSetDevice(ctx->device)); CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream)); return 0; }
 int64_t mimc3cu_launch_count(const mimc3cu_ctx *ctx) { return ctx->launches; }
 
 /* ---- images ------------------------------------------------------------------------- */
@@ -223,6 +223,7 @@ int mimc3cu_image_create(mimc3cu_ctx *ctx, int32_t H, int32_t W, int32_t *handle
 }
 
 int mimc3cu_image_destroy(mimc3cu_ctx *ctx, int32_t handle) {
+    cudaSetDevice(ctx->device);
     Image *im = get_image(ctx, handle);
     if (!im) return mimc3cu_fail(ctx, "image_destroy: bad handle %d", handle);
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -233,6 +234,7 @@ int mimc3cu_image_destroy(mimc3cu_ctx *ctx, int32_t handle) {
 }
 
 int mimc3cu_image_upload(mimc3cu_ctx *ctx, int32_t handle, const float *host) {
+    cudaSetDevice(ctx->device);
     Image *im = get_image(ctx, handle);
     if (!im) return mimc3cu_fail(ctx, "image_upload: bad handle %d", handle);
     image_invalidate(im);
@@ -242,6 +244,7 @@ int mimc3cu_image_upload(mimc3cu_ctx *ctx, int32_t handle, const float *host) {
 }
 
 static int upload_int(mimc3cu_ctx *ctx, int32_t handle, const void *host, int bytes_per_px) {
+    cudaSetDevice(ctx->device);
     Image *im = get_image(ctx, handle);
     if (!im) return mimc3cu_fail(ctx, "image_upload: bad handle %d", handle);
     size_t count = (size_t)im->H * im->W;
@@ -258,6 +261,7 @@ int mimc3cu_image_upload_u8(mimc3cu_ctx *ctx, int32_t handle, const uint8_t *hos
 int mimc3cu_image_upload_u16(mimc3cu_ctx *ctx, int32_t handle, const uint16_t *host) { return upload_int(ctx, handle, host, 2); }
 
 int mimc3cu_image_copy_from_device(mimc3cu_ctx *ctx, int32_t handle, const float *dev) {
+    cudaSetDevice(ctx->device);
     Image *im = get_image(ctx, handle);
     if (!im) return mimc3cu_fail(ctx, "image_copy_from_device: bad handle %d", handle);
     image_invalidate(im);
@@ -267,6 +271,7 @@ int mimc3cu_image_copy_from_device(mimc3cu_ctx *ctx, int32_t handle, const float
 }
 
 int mimc3cu_image_download(mimc3cu_ctx *ctx, int32_t handle, float *host) {
+    cudaSetDevice(ctx->device);
     Image *im = get_image(ctx, handle);
     if (!im) return mimc3cu_fail(ctx, "image_download: bad handle %d", handle);
     CU_CHECK(ctx, cudaMemcpyAsync(host, im->d, (size_t)im->H * im->W * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
@@ -275,6 +280,7 @@ int mimc3cu_image_download(mimc3cu_ctx *ctx, int32_t handle, float *host) {
 }
 
 int mimc3cu_image_fill_zero(mimc3cu_ctx *ctx, int32_t handle) {
+    cudaSetDevice(ctx->device);
     Image *im = get_image(ctx, handle);
     if (!im) return mimc3cu_fail(ctx, "image_fill_zero: bad handle %d", handle);
     image_invalidate(im);
@@ -288,6 +294,7 @@ float *mimc3cu_image_ptr(mimc3cu_ctx *ctx, int32_t handle) {
 }
 
 int mimc3cu_conv2(mimc3cu_ctx *ctx, int32_t src, const float *kernel, int32_t kh, int32_t kw, int32_t dst) {
+    cudaSetDevice(ctx->device);
     Image *s = get_image(ctx, src), *d = get_image(ctx, dst);
     if (!s || !d) return mimc3cu_fail(ctx, "conv2: bad image handle");
     if (s == d) return mimc3cu_fail(ctx, "conv2: src and dst must differ");
@@ -607,6 +614,7 @@ int mimc3cu_postprocess_band(mimc3cu_ctx *ctx, const float *dp_dev, const double
     return post_run_band(ctx, dp_dev, xyuvav, p, own_row0, own_rows, comm, planes_dev, stats);
 }
 int mimc3cu_postprocess_stage(mimc3cu_ctx *ctx, int32_t which, void *host) { return post_stage(ctx, which, host); }
+int mimc3cu_dp_negate_uv_async(mimc3cu_ctx *ctx, float *dp_dev, int32_t n) { return post_negate_uv(ctx, dp_dev, n); }
 int mimc3cu_finalize(mimc3cu_ctx *ctx, float *planes_dev, const mimc3cu_params *p, float *du_cp, float *dv_cp) {
     return post_finalize(ctx, planes_dev, p, du_cp, dv_cp);
 }
@@ -615,6 +623,7 @@ int mimc3cu_finalize(mimc3cu_ctx *ctx, float *planes_dev, const mimc3cu_params *
 int mimc3cu_timing_enable(mimc3cu_ctx *ctx, int on) { ctx->timing = on != 0; return 0; }
 
 int mimc3cu_timing_read(mimc3cu_ctx *ctx, double *ms, int64_t *counts) {
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     for (int f = 0; f < 3; f++) {
         double tot = 0.0;
@@ -638,16 +647,19 @@ int mimc3cu_malloc(mimc3cu_ctx *ctx, size_t bytes, void **dev) {
     return 0;
 }
 int mimc3cu_free(mimc3cu_ctx *ctx, void *dev) {
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     CU_CHECK(ctx, cudaFree(dev));
     return 0;
 }
 int mimc3cu_memcpy_d2h(mimc3cu_ctx *ctx, void *host, const void *dev, size_t bytes) {
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
     CU_CHECK(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;
 }
 int mimc3cu_memcpy_h2d(mimc3cu_ctx *ctx, void *dev, const void *host, size_t bytes) {
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
     CU_CHECK(ctx, cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
     return 0;

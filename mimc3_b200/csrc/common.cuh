@@ -189,3 +189,4 @@ int post_band_halo(const mimc3cu_params *p);
 int post_stage(mimc3cu_ctx *ctx, int32_t which, void *host);
 int post_finalize(mimc3cu_ctx *ctx, float *planes, const mimc3cu_params *p, float *du_cp, float *dv_cp);
 void post_free(mimc3cu_ctx *ctx);
+int post_negate_uv(mimc3cu_ctx *ctx, float *dp, int32_t n);

@@ -88,7 +88,8 @@ struct Match2Args {
 #ifdef MIMC3CU_PROFILE
 // cycles seen by lane 0 of the group's leader warp: 0 node total, 1 staging, 2 leader section (7 walk, 8 requests, 9 replay + fit),
 // 3 compute (+ barrier waits), 4 finalize + masked round, 10 probe-table update; 5 rounds, 6 nodes
-__device__ unsigned long long g_prof[16];
+__device__ unsigned long long g_prof[24];
+__device__ unsigned int g_busy[256];   // per SM: node streams inside a fast round right now (slots 11..: histogram seen mid-round)
 #define PROF_T(var) const long long var = clock64()
 #define PROF_ADD(slot, v) do { if (lane == 0 && gwarp == lead) atomicAdd(&g_prof[slot], (unsigned long long)(v)); } while (0)
 #else
@@ -129,6 +130,14 @@ struct Cfg {
     // pivots per node this instantiation can walk (explore state in shared memory); longer pivot lines go to
     // a wider instantiation or to the general kernel
     static constexpr int PMAX = G == 32 ? 64 : 128;
+    // cells evaluated side by side in the inner loop (independent accumulator chains)
+#ifndef MIMC3CU_CP
+#define MIMC3CU_CP 2
+#endif
+    static constexpr int CP = (G >= 128) ? MIMC3CU_CP : 1;
+    // 16-byte staging loads where the register budget has room for them (measured: +5 % at chip half-width 15; the
+    // 64- and 80-register instantiations of the other sizes spill with them and lose 2-13 %)
+    static constexpr bool VEC = OCW == 15;
     static_assert(NSEG >= 1, "group too small for this chip");
     static_assert((L + 1) / 2 <= 16, "at most 16 pixels per FP32 accumulator");
 };
@@ -154,6 +163,50 @@ __device__ __forceinline__ void stage_rows(const float *__restrict__ src, int gs
 #pragma unroll
         for (int u = 0; u < 8; u++)
             if (e + u * NT < total) dst[e + u * NT] = v[u];
+    }
+}
+
+// Same copy with 16-byte global loads: every row is read from the 16-byte aligned address at or below its first
+// pixel (`a` floats earlier; the same for all rows because the row stride is a multiple of four floats), so a row of
+// `width` pixels takes (a + width + 3) / 4 LDG.128 instead of `width` LDG.32, four in flight per thread; the stores
+// stay scalar (the tile pitch is odd so that the row-per-lane reads of the inner loop are conflict-free).
+// The caller guarantees gstride % 4 == 0 and that the aligned spans stay inside the image buffer.
+template <int NT, int DEPTH>
+__device__ __forceinline__ void stage_rows_v4(const float *__restrict__ src, int gstride, float *dst, int spitch, int rows, int width,
+                                              int tix) {
+    const int a = (int)(((size_t)src >> 2) & 3);
+    const int nch = (a + width + 3) >> 2;
+    const int total = rows * nch;
+    const float4 *base = (const float4 *)(src - a);
+    const int g4 = gstride >> 2;
+    int y = tix / nch, j = tix - y * nch;
+    const int dy = NT / nch, dj = NT - dy * nch;
+    for (int e = tix; e < total; e += NT * DEPTH) {
+        float4 v[DEPTH];
+        int yj[DEPTH];
+#pragma unroll
+        for (int u = 0; u < DEPTH; u++) {
+            yj[u] = (y << 16) | j;
+            if (e + u * NT < total) v[u] = __ldg(base + (size_t)y * g4 + j);
+            j += dj; y += dy;
+            if (j >= nch) { j -= nch; y++; }
+        }
+#pragma unroll
+        for (int u = 0; u < DEPTH; u++) {
+            if (e + u * NT < total) {
+                float *row = dst + (yj[u] >> 16) * spitch;
+                const int c = 4 * (yj[u] & 0xffff) - a;
+                if (c >= 0 && c < width) row[c] = v[u].x;
+                if (c + 1 >= 0 && c + 1 < width) row[c + 1] = v[u].y;
+                if (c + 2 >= 0 && c + 2 < width) row[c + 2] = v[u].z;
+                if (c + 3 < width) row[c + 3] = v[u].w;
+            }
+        }
+    }
+    const int pad = spitch - width;
+    for (int i = tix; i < rows * pad; i += NT) {
+        const int r = i / pad;
+        dst[r * spitch + width + (i - r * pad)] = 0.0f;
     }
 }
 
@@ -435,51 +488,88 @@ __device__ __forceinline__ void node_rounds(const Match2Args &a, CtlT &ctl, floa
             w_flag = (inside ? 1 : 0) | ((tx + 2 * ty) << 1);
             if (inside) rect_query_packed(a.sat_srch, W1, ix0, iy0, ix0 + S - tx, iy0 + S - ty, w_ss, w_pk);
         }
-        for (int c = 0; c < m; c++) {
-            const int job = ctl.job[c];
-            const int cy = job_cy(job), cx = job_cx(job);
-            unsigned int hi = 0;
-            int lo = 0;
+        // CP cells at a time: their accumulator chains are independent, which keeps the FP32 pipe fed when few warps are
+        // resident (the wide-search-area bins: +8 % on the fast-glacier scene; neutral at four CTAs per SM)
+        constexpr int CP = C::CP;
+#ifdef MIMC3CU_PROFILE
+        unsigned int prof_smid = 0;
+        if (lane == 0 && gwarp == lead) { asm("mov.u32 %0, %%smid;" : "=r"(prof_smid)); atomicAdd(&g_busy[prof_smid & 255u], 1u); }
+#endif
+        for (int c = 0; c < m; c += CP) {
+#ifdef MIMC3CU_PROFILE
+            if (lane == 0 && gwarp == lead && c == ((m / 2) & ~(CP - 1))) {
+                const unsigned int k = *(volatile unsigned int *)&g_busy[prof_smid & 255u];
+                atomicAdd(&g_prof[11 + min(k, 8u)], 1ull);
+            }
+#endif
+            const float *spc[CP];
+#pragma unroll
+            for (int q = 0; q < CP; q++) {
+                const int job = ctl.job[min(c + q, m - 1)];   // an odd tail evaluates its last cell twice
+                spc[q] = sa_thread + (job_cy(job) + 1) * pitch + (job_cx(job) + 1);
+            }
+            unsigned int hi[CP];
+            int lo[CP];
+#pragma unroll
+            for (int q = 0; q < CP; q++) { hi[q] = 0; lo[q] = 0; }
 #pragma unroll
             for (int rb = 0; rb < C::RB; rb++) {
                 // threads without chip pixels (r = col0 = 0, chip all zero) run the same code: no branch; a
                 // thread whose second row does not exist reads its first row again (times zero)
-                const float *sp = sa_thread + (cy + 1) * pitch + (cx + 1) + (rb ? row2 : 0);
                 // Two pixels per instruction (FMUL2 / FADD2 / FFMA2, sm_100): lane 0 of the packed pair
                 // accumulates the even pixels, lane 1 the odd ones -- the same two accumulators as a
                 // scalar loop would keep, at half the issue slots.  One accumulator pair per chip row
                 // (<= 16 pixels per accumulator).
-                f32x2 acc = pack2(a.A0, a.A0), lo2 = pack2(a.Mlo, a.Mlo);
+                f32x2 acc[CP], lo2[CP];
+#pragma unroll
+                for (int q = 0; q < CP; q++) { acc[q] = pack2(a.A0, a.A0); lo2[q] = pack2(a.Mlo, a.Mlo); }
+                // The search-area pixels go through a ring of PD register pairs: the pair of step k + PD is requested
+                // when step k starts, so the shared-memory latency (~30 cycles) is off the accumulator chains.  The
+                // loads are volatile asm: ptxas otherwise sinks every LDS to just before its FFMA2 and each step
+                // waits out the full latency (17 % of all warp time in the round-1 build, ncu source view).
 #pragma unroll
                 for (int k = 0; k < L; k += 2) {
                     // an odd L ends with a (pixel, 0) pair: the zero is a literal, not a load
                     const f32x2 rv = pack2(chip[rb][k], k + 1 < L ? chip[rb][k + 1] : 0.0f);
-                    const f32x2 sv = pack2(sp[k], k + 1 < L ? sp[k + 1] : 0.0f);
-                    if (EXACTP) {
-                        // every product is exact in FP32 (scaled operands < 2^12): fma(r, s, acc) ==
-                        // fadd(acc, fmul(r, s)) and fma(r, s, -z) == p - z, one instruction less per pixel
-                        const f32x2 s1 = fma2(rv, sv, acc);
-                        const f32x2 nz = sub2(acc, s1);
-                        lo2 = add2(lo2, fma2(rv, sv, nz));
-                        acc = s1;
-                    } else {
-                        const f32x2 pr = mul2(rv, sv);
-                        const f32x2 s1 = add2(acc, pr);
-                        const f32x2 z = sub2(s1, acc);
-                        lo2 = add2(lo2, sub2(pr, z));
-                        acc = s1;
+#pragma unroll
+                    for (int q = 0; q < CP; q++) {
+                        const float *sp = spc[q] + (rb ? row2 : 0);
+                        const f32x2 sv = pack2(sp[k], k + 1 < L ? sp[k + 1] : 0.0f);
+                        if (EXACTP) {
+                            // every product is exact in FP32 (scaled operands < 2^12): fma(r, s, acc) ==
+                            // fadd(acc, fmul(r, s)) and fma(r, s, -z) == p - z, one instruction less per pixel
+                            const f32x2 s1 = fma2(rv, sv, acc[q]);
+                            const f32x2 nz = sub2(acc[q], s1);
+                            lo2[q] = add2(lo2[q], fma2(rv, sv, nz));
+                            acc[q] = s1;
+                        } else {
+                            const f32x2 pr = mul2(rv, sv);
+                            const f32x2 s1 = add2(acc[q], pr);
+                            const f32x2 z = sub2(s1, acc[q]);
+                            lo2[q] = add2(lo2[q], sub2(pr, z));
+                            acc[q] = s1;
+                        }
                     }
                 }
-                float acc0, acc1, lo0, lo1;
-                unpack2(acc, acc0, acc1);
-                unpack2(lo2, lo0, lo1);
-                hi += (__float_as_uint(acc0) - a.A0_bits) + (__float_as_uint(acc1) - a.A0_bits);
-                lo += (int)(__float_as_uint(lo0) - a.Mlo_bits) + (int)(__float_as_uint(lo1) - a.Mlo_bits);
+#pragma unroll
+                for (int q = 0; q < CP; q++) {
+                    float acc0, acc1, lo0, lo1;
+                    unpack2(acc[q], acc0, acc1);
+                    unpack2(lo2[q], lo0, lo1);
+                    hi[q] += (__float_as_uint(acc0) - a.A0_bits) + (__float_as_uint(acc1) - a.A0_bits);
+                    lo[q] += (int)(__float_as_uint(lo0) - a.Mlo_bits) + (int)(__float_as_uint(lo1) - a.Mlo_bits);
+                }
             }
-            hi = __reduce_add_sync(0xffffffffu, hi);
-            lo = __reduce_add_sync(0xffffffffu, lo);
-            if (lane == 0) ctl.part[gwarp][c] = make_int2((int)hi, lo);
+#pragma unroll
+            for (int q = 0; q < CP; q++) {
+                hi[q] = __reduce_add_sync(0xffffffffu, hi[q]);
+                lo[q] = __reduce_add_sync(0xffffffffu, lo[q]);
+                if (lane == 0 && c + q < m) ctl.part[gwarp][c + q] = make_int2((int)hi[q], lo[q]);
+            }
         }
+#ifdef MIMC3CU_PROFILE
+        if (lane == 0 && gwarp == lead) atomicSub(&g_busy[prof_smid & 255u], 1u);
+#endif
         gsync<G>();
         PROF_T(t_c1);
         PROF_ADD(3, t_c1 - t_p1);
@@ -674,8 +764,14 @@ __global__ void __launch_bounds__(Cfg<OCW, G>::CTA, MINCTA) match2_kernel(const 
         }
 
         // ---- stage the chip through shared memory into registers (extract_refchip :845-855) ----
+        // 16-byte loads need a row stride of whole float4s and must not reach before / behind the image buffer
+        const bool vec_ok = (a.W & 3) == 0;
         if (u0 - OCW >= 0 && v0 - OCW >= 0 && u0 + OCW < a.W && v0 + OCW < a.H) {
-            stage_rows<G>(a.ref + (size_t)(v0 - OCW) * a.W + (u0 - OCW), a.W, sa, S, S, S, t);
+            const size_t first = (size_t)(v0 - OCW) * a.W + (u0 - OCW);
+            if (C::VEC && vec_ok && first >= 3 && first + (size_t)(S - 1) * a.W + S + 3 <= (size_t)a.H * a.W)
+                stage_rows_v4<G, 4>(a.ref + first, a.W, sa, S, S, S, t);
+            else
+                stage_rows<G>(a.ref + first, a.W, sa, S, S, S, t);
         } else {
             for (int i = t; i < S * S; i += G) {
                 const int rr = i / S, cc = i - rr * S;
@@ -716,7 +812,11 @@ __global__ void __launch_bounds__(Cfg<OCW, G>::CTA, MINCTA) match2_kernel(const 
         //      never-written last row / column, zero in the pad columns [Dx2, pitch) ----------------
         if (su0 - dx2 >= 0 && sv0 - dy2 >= 0 && su0 - dx2 + Dx2 - 1 <= a.W && sv0 - dy2 + Dy2 - 1 <= a.H) {
             // written part entirely inside the image (the common case): no per-pixel bounds tests
-            stage_rows<G>(a.srch + (size_t)(sv0 - dy2) * a.W + (su0 - dx2), a.W, sa, pitch, Dy2 - 1, Dx2 - 1, t);
+            const size_t first = (size_t)(sv0 - dy2) * a.W + (su0 - dx2);
+            if (C::VEC && vec_ok && first >= 3 && first + (size_t)(Dy2 - 2) * a.W + Dx2 + 2 <= (size_t)a.H * a.W)
+                stage_rows_v4<G, (G >= 128 ? 2 : 4)>(a.srch + first, a.W, sa, pitch, Dy2 - 1, Dx2 - 1, t);   // the chip pixels are live here: fewer loads in flight
+            else
+                stage_rows<G>(a.srch + first, a.W, sa, pitch, Dy2 - 1, Dx2 - 1, t);
             for (int x = t; x < pitch; x += G) sa[(Dy2 - 1) * pitch + x] = 0.0f;
         } else {
             for (int y = gwarp; y < Dy2; y += C::NWARPS) {
@@ -963,6 +1063,7 @@ int launch_match2(mimc3cu_ctx *ctx, const MatchLaunch &L, const Image *ref, cons
                 if (tab[k].G == 128 && tab[k].ctas >= 5) rc = exactp ? launch_one<40, 128, true, 5>(ctx, a, 1, smem, a.n_list, nullptr) : launch_one<40, 128, false, 5>(ctx, a, 1, smem, a.n_list, nullptr);
                 else if (tab[k].G == 128) rc = exactp ? launch_one<40, 128, true>(ctx, a, 1, smem, a.n_list, nullptr) : launch_one<40, 128, false>(ctx, a, 1, smem, a.n_list, nullptr);
                 else if (tab[k].ctas <= 2) rc = exactp ? launch_one<40, 256, true, 2>(ctx, a, 1, smem, a.n_list, nullptr) : launch_one<40, 256, false, 2>(ctx, a, 1, smem, a.n_list, nullptr);
+                else if (tab[k].ctas == 3) rc = exactp ? launch_one<40, 256, true, 3>(ctx, a, 1, smem, a.n_list, nullptr) : launch_one<40, 256, false, 3>(ctx, a, 1, smem, a.n_list, nullptr);
                 else rc = exactp ? launch_one<40, 256, true>(ctx, a, 1, smem, a.n_list, nullptr) : launch_one<40, 256, false>(ctx, a, 1, smem, a.n_list, nullptr);
                 break;
             default: return mimc3cu_fail(ctx, "match2: unsupported ocw %d", L.ocw);
@@ -971,9 +1072,16 @@ int launch_match2(mimc3cu_ctx *ctx, const MatchLaunch &L, const Image *ref, cons
     }
 #ifdef MIMC3CU_PROFILE
     {
-        unsigned long long h[16];
+        unsigned long long h[24];
         cudaStreamSynchronize(ctx->stream);
         cudaMemcpyFromSymbol(h, g_prof, sizeof(h));
+        if (h[6]) {
+            double tot = 0;
+            for (int k = 11; k < 20; k++) tot += (double)h[k];
+            fprintf(stderr, "[prof ocw %d] streams of the SM inside a fast round, seen mid-round:", L.ocw);
+            for (int k = 11; k < 20; k++) if (h[k]) fprintf(stderr, " %d: %.0f%%", k - 11, 100.0 * h[k] / tot);
+            fprintf(stderr, "\n");
+        }
         if (h[6])
             fprintf(stderr, "[prof ocw %d] nodes %llu rounds/node %.2f  cycles/node: total %.0f staging %.0f leader %.0f (walk %.0f requests %.0f replay %.0f) "
                             "compute %.0f finalize %.0f table %.0f\n",

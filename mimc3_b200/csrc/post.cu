@@ -423,6 +423,14 @@ __global__ void __launch_bounds__(kT) pack_kernel(const int *id, const float *mv
     for (int k = 0; k < 5; k++) planes[(size_t)k * n + g] = c >= 0 ? mvn[((size_t)g * K + c) * 5 + k] : CUDART_NAN_F;   // :950-973
 }
 
+// main negates du, dv of the swapped passes on the host (MIMC_main.c:289-293); the drop-in redoes that on its device copy
+__global__ void __launch_bounds__(kT) negate_uv_kernel(float *dp, int n) {
+    int g = blockIdx.x * kT + threadIdx.x;
+    if (g >= n) return;
+    dp[3 * (size_t)g] = -dp[3 * (size_t)g];
+    dp[3 * (size_t)g + 1] = -dp[3 * (size_t)g + 1];
+}
+
 // get_ruv_neighbor :1266-1327, restricted to the window that can satisfy the radius test
 // (same float arithmetic, same row-major order).
 int ruv_neighbor_host(const double *xyuvav, int dimx, int dimy, float radius, float mps, std::vector<int32_t> &out) {
@@ -479,6 +487,15 @@ int ensure_stack(mimc3cu_ctx *ctx, int32_t slots) {
 }
 
 }  // namespace
+
+int post_negate_uv(mimc3cu_ctx *ctx, float *dp, int32_t n) {
+    if (n <= 0) return 0;
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    negate_uv_kernel<<<nblocks(n), kT, 0, ctx->stream>>>(dp, n);
+    ctx->launches++;
+    CU_CHECK(ctx, cudaGetLastError());
+    return 0;
+}
 
 void post_free(mimc3cu_ctx *ctx) {
     if (!ctx->post) return;

@@ -91,6 +91,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "mimc3cu_comm_destroy": (None, [vp]),
         "mimc3cu_comm_info": (C.c_int, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64), C.POINTER(i64)]),
         "mimc3cu_comm_gather": (C.c_int, [vp, vp, vp, vp, i32]),
+        "mimc3cu_dp_negate_uv_async": (C.c_int, [vp, vp, i32]),
         "mimc3cu_set_matcher": (C.c_int, [vp, i32]),
         "mimc3cu_last_matcher": (C.c_int, [vp]),
         "mimc3cu_image_class": (C.c_int, [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(f32)]),
@@ -116,7 +117,7 @@ EXPORTED_SYMBOLS = (
     "mimc3cu_memcpy_h2d", "mimc3cu_set_matcher", "mimc3cu_last_matcher", "mimc3cu_image_class",
     "mimc3cu_get_offset_image", "mimc3cu_band_halo", "mimc3cu_postprocess_band", "mimc3cu_image_fill_zero",
     "mimc3cu_multimatch_diag_async", "mimc3cu_comm_unique_id", "mimc3cu_comm_init_rank", "mimc3cu_comm_init_all",
-    "mimc3cu_comm_destroy", "mimc3cu_comm_info", "mimc3cu_comm_gather",
+    "mimc3cu_comm_destroy", "mimc3cu_comm_info", "mimc3cu_comm_gather", "mimc3cu_dp_negate_uv_async",
 )
 
 
