@@ -454,12 +454,16 @@ def main():
         bp, st, comm = pl.postprocess_band(d, gxy, gparams, row0, rows, transport)
         comm_stats["halo_exchanges"] += comm.n_exchanges; comm_stats["allreduces"] += comm.n_allreduce; comm_stats["steps_counted"] += 1
         with torch.cuda.stream(stream):
-            if len(set(r for _, r in band_rows)) == 1:
-                parts = transport.gather_rows(bp, dst=0)
-                if rank == 0:
-                    torch.cat(parts, dim=1, out=planes)
+            # final gather of the five planes (bands may differ in size: point-to-point)
+            if rank == 0:
+                planes[:, row0:row0 + rows].copy_(bp)
+                for r in range(1, world):
+                    r0, rr = band_rows[r]
+                    for k in range(5):
+                        dist.recv(planes[k, r0:r0 + rr], src=r)
             else:
-                raise SystemExit("bench.py: --band-comm python needs equal bands (use the default nccl communicator)")
+                for k in range(5):
+                    dist.send(bp[k].contiguous(), dst=0)
         return st
 
     def step(collect_ncell=False):

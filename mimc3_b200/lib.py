@@ -166,6 +166,19 @@ def comm_unique_id() -> bytes:
     return buf.raw
 
 
+def comm_init_all(contexts) -> None:
+    """One process driving several GPUs: attach an NCCL communicator to every context (rank = list position).
+    The bands' collective calls must then be issued from one host thread per context."""
+    L = load_library()
+    arr = (C.c_void_p * len(contexts))(*[c.h for c in contexts])
+    if L.mimc3cu_comm_init_all(arr, len(contexts)):
+        raise Mimc3CuError(L.mimc3cu_last_error(contexts[0].h).decode())
+
+
+def device_count() -> int:
+    return int(load_library().mimc3cu_device_count())
+
+
 def get_uv_pivot(xyuvav, dt, mpp, ocw, H, W, aw_sf=1.8, aw_cre=10.0):
     """get_uv_pivot (MIMC_module.c:543-602) -> CSR (off[n+1], piv[total,2])."""
     L = load_library()

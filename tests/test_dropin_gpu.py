@@ -20,9 +20,9 @@ DROPIN_CLI = os.path.join(REF_DIR, "MIMC3_dropin")
 FAKETIME = os.path.join(REF_DIR, "libfaketime.so")
 
 
-def run_cli(binary, workdir, outdir, fake_time):
+def run_cli(binary, workdir, outdir, fake_time, **extra_env):
     os.makedirs(outdir, exist_ok=True)
-    env = dict(os.environ, MIMC3_FAKE_TIME=str(fake_time), LD_PRELOAD=FAKETIME)
+    env = dict(os.environ, MIMC3_FAKE_TIME=str(fake_time), LD_PRELOAD=FAKETIME, **extra_env)
     args = [binary, os.path.join(workdir, "20200101000000_i0.tif"), os.path.join(workdir, "20200117000000_i1.tif"),
             os.path.join(workdir, "xyuvav.GMA"), outdir]
     r = subprocess.run(args, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
@@ -70,3 +70,25 @@ def test_unchanged_driver_with_the_cuda_module_writes_the_same_files(tmp_path, d
         assert np.allclose(a[k], b[k], rtol=1e-5, atol=1e-4, equal_nan=True), (k, np.nanmax(np.abs(a[k] - b[k])))
         assert (a[k] == b[k])[~np.isnan(a[k])].mean() > 0.98, k
     assert abs(float(a["meta"]["cp_offset_subint_u"]) - float(b["meta"]["cp_offset_subint_u"])) < 1e-4
+
+
+def test_unchanged_driver_on_two_gpus(tmp_path):
+    """MIMC3CU_DEVICES=2: the same unchanged driver, node rows sharded over two GPUs inside the drop-in (one context and
+    one host thread per GPU, banded postprocess over the library's NCCL communicator) writes the files of the one-GPU run."""
+    from mimc3_b200 import lib
+    for f in (DROPIN_CLI, FAKETIME):
+        if not os.path.exists(f):
+            pytest.skip(f"{f} not built (needs the container with /root/reference)")
+    if lib.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sc = small_scene(H=800, W=640, seed=72, spacing=22, dtype="u16", null_wedge=True, decorrelated_patches=8, offset=(1, 2))
+    work = str(tmp_path)
+    synth.write_tiff(os.path.join(work, "20200101000000_i0.tif"), sc.i0.numpy().astype(np.uint16))
+    synth.write_tiff(os.path.join(work, "20200117000000_i1.tif"), sc.i1.numpy().astype(np.uint16))
+    synth.write_gma(os.path.join(work, "xyuvav.GMA"), sc.xyuvav)
+    run_cli(DROPIN_CLI, work, os.path.join(work, "out_1"), 1700000555)
+    run_cli(DROPIN_CLI, work, os.path.join(work, "out_2"), 1700000555, MIMC3CU_DEVICES="2")
+    a, b = read_outputs(os.path.join(work, "out_1")), read_outputs(os.path.join(work, "out_2"))
+    for k in ("vx", "vy", "ex", "ey", "qual", "flagcp", "x", "y"):
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+    assert a["meta"] == b["meta"]
