@@ -487,6 +487,8 @@ def main():
 
     sampler = ClockSampler(local_rank)
     ctx.timing_enable(True); ctx.timing_read()
+    if world > 1 and transport is None:
+        ctx.comm_timing(True)
     barrier()
     sampler.start()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
@@ -499,6 +501,8 @@ def main():
     ms_total = e0.elapsed_time(e1)
     fam_ms, fam_cnt = ctx.timing_read()
     ctx.timing_enable(False)
+    comm_ms = ctx.comm_timing(False) if (world > 1 and transport is None) else None
+    comm_calls = dict(comm_stats)
     launches = ctx.launch_count() - launches0
     if dist is not None:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -618,7 +622,9 @@ def main():
                 "roofline": roofline, "cpu_baseline": cpu, "parity": parity, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
                 "collectives": (dict(comm_stats, backend="nccl", issued_by=("libmimc3cu.so (ncclSend/ncclRecv/ncclAllReduce on the context stream)" if transport is None else "bands.py callbacks over torch.distributed"),
                                      pattern="neighbour halo rows + int32 counter all-reduce per sweep, final gather of 5 planes",
-                                     postprocess_ms_per_step=fam_ms[2] / max(1, args.steps)) if world > 1 else None),
+                                     postprocess_ms_per_step=fam_ms[2] / max(1, args.steps),
+                                     halo_exchange_ms_per_step=(comm_ms[0] / args.steps if comm_ms else None),
+                                     allreduce_ms_per_step=(comm_ms[1] / args.steps if comm_ms else None)) if world > 1 else None),
                 "planes_sha256": planes_digest,
                 "postprocess_stats": {"dpf1_sweeps": int(stats[0]), "pseudosmoothing_sweeps": int(stats[1]), "holes_after_dpf0": int(stats[2])} if stats is not None else None}
         emit_json(line)

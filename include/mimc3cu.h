@@ -87,8 +87,11 @@ int mimc3cu_image_copy_from_device(mimc3cu_ctx *ctx, int32_t handle, const float
 int mimc3cu_image_download(mimc3cu_ctx *ctx, int32_t handle, float *host);
 /* Zero the payload (asynchronous on the context stream). */
 int mimc3cu_image_fill_zero(mimc3cu_ctx *ctx, int32_t handle);
-/* Raw device pointer of the image payload. */
-float *mimc3cu_image_ptr(mimc3cu_ctx *ctx, int32_t handle);
+/* Raw device pointer of the image payload, read-only: the matcher caches statistics and a summed-area table per
+ * image.  Whoever writes the payload behind the library's back (casting the const away) must call
+ * mimc3cu_image_invalidate afterwards, or the exact-FP32 matcher works with the old table. */
+const float *mimc3cu_image_ptr(mimc3cu_ctx *ctx, int32_t handle);
+int mimc3cu_image_invalidate(mimc3cu_ctx *ctx, int32_t handle);
 
 /* GMA_float_conv2, MIMC_module.c:2517-2585.  dst is updated IN PLACE with the
  * reference's stale-border semantics.  kernel is (kh, kw) row-major
@@ -231,6 +234,10 @@ void mimc3cu_comm_destroy(mimc3cu_ctx *ctx);
 /* rank / world and the number of halo exchanges / all-reduces issued so far (any pointer may be NULL); non-zero
  * without a communicator. */
 int mimc3cu_comm_info(const mimc3cu_ctx *ctx, int32_t *rank, int32_t *world, int64_t *exchanges, int64_t *allreduces);
+/* Device time of the collectives (CUDA events around them on the context's stream) since the last call: summed
+ * milliseconds of the halo exchanges (incl. the dirty-flag OR) and of the counter all-reduces; `on` switches the
+ * bracketing on / off for what follows.  Synchronises the stream. */
+int mimc3cu_comm_timing(mimc3cu_ctx *ctx, int32_t on, double *exchange_ms, double *allreduce_ms);
 /* The final gather: rank r contributes bytes[r] bytes from the device buffer `send`; on `root` the device buffer
  * `recv` receives them back to back in rank order.  Asynchronous on the context's stream. */
 int mimc3cu_comm_gather(mimc3cu_ctx *ctx, const void *send, const int64_t *bytes, void *recv, int32_t root);

@@ -50,6 +50,7 @@ static cudaEvent_t take_event(mimc3cu_ctx *ctx) {
 
 ScopedTimer::ScopedTimer(mimc3cu_ctx *c, int fam) : ctx(c), family(fam) {
     if (!ctx->timing) return;
+    if (ctx->timers[fam].size() >= 65536) return;   // nobody reads them: stop recording instead of growing without bound
     cudaEvent_t start = take_event(ctx);
     stop = take_event(ctx);
     cudaEventRecord(start, ctx->stream);
@@ -288,9 +289,16 @@ int mimc3cu_image_fill_zero(mimc3cu_ctx *ctx, int32_t handle) {
     return 0;
 }
 
-float *mimc3cu_image_ptr(mimc3cu_ctx *ctx, int32_t handle) {
+const float *mimc3cu_image_ptr(mimc3cu_ctx *ctx, int32_t handle) {
     Image *im = get_image(ctx, handle);
     return im ? im->d : nullptr;
+}
+
+int mimc3cu_image_invalidate(mimc3cu_ctx *ctx, int32_t handle) {
+    Image *im = get_image(ctx, handle);
+    if (!im) return mimc3cu_fail(ctx, "image_invalidate: bad handle %d", handle);
+    image_invalidate(im);
+    return 0;
 }
 
 int mimc3cu_conv2(mimc3cu_ctx *ctx, int32_t src, const float *kernel, int32_t kh, int32_t kw, int32_t dst) {
@@ -313,13 +321,20 @@ int64_t mimc3cu_get_uv_pivot(const double *xyuvav, int32_t n, float dt, float mp
     // times per node; the steps of the sizing call are kept for the immediately following fill call.
     struct Cache {
         const double *xy = nullptr; int32_t n = 0, ocw = 0, H = 0, W = 0; float dt = 0, mpp = 0, sf = 0, cre = 0;
-        double first_row[6] = {0, 0, 0, 0, 0, 0};
+        double first_row[6] = {0, 0, 0, 0, 0, 0}, mid_row[6] = {0, 0, 0, 0, 0, 0}, last_row[6] = {0, 0, 0, 0, 0, 0};
         std::vector<PivotStep> steps;
     };
     static thread_local Cache cache;
+    // the fill call must follow the sizing call for the same array: first, middle and last row are compared as well
+    // (an array edited in place between the two calls falls back to recomputing the steps)
+    auto rows_match = [&] {
+        return memcmp(cache.first_row, xyuvav, sizeof(cache.first_row)) == 0 &&
+               memcmp(cache.mid_row, xyuvav + 6 * (size_t)(n / 2), sizeof(cache.mid_row)) == 0 &&
+               memcmp(cache.last_row, xyuvav + 6 * (size_t)(n - 1), sizeof(cache.last_row)) == 0;
+    };
     const bool hit = piv && cache.xy == xyuvav && cache.n == n && cache.ocw == ocw && cache.H == H && cache.W == W &&
                      cache.dt == dt && cache.mpp == mpp && cache.sf == AW_SF && cache.cre == AW_CRE && n > 0 &&
-                     memcmp(cache.first_row, xyuvav, sizeof(cache.first_row)) == 0 && cache.steps.size() == (size_t)n;
+                     cache.steps.size() == (size_t)n && rows_match();
     if (!hit) {
         cache.steps.resize((size_t)n);
         PivotStep *out = cache.steps.data();   // NOT `cache` inside the workers: it is thread_local
@@ -328,7 +343,11 @@ int64_t mimc3cu_get_uv_pivot(const double *xyuvav, int32_t n, float dt, float mp
         });
         cache.xy = xyuvav; cache.n = n; cache.ocw = ocw; cache.H = H; cache.W = W;
         cache.dt = dt; cache.mpp = mpp; cache.sf = AW_SF; cache.cre = AW_CRE;
-        if (n > 0) memcpy(cache.first_row, xyuvav, sizeof(cache.first_row));
+        if (n > 0) {
+            memcpy(cache.first_row, xyuvav, sizeof(cache.first_row));
+            memcpy(cache.mid_row, xyuvav + 6 * (size_t)(n / 2), sizeof(cache.mid_row));
+            memcpy(cache.last_row, xyuvav + 6 * (size_t)(n - 1), sizeof(cache.last_row));
+        }
     }
     const PivotStep *steps = cache.steps.data();
     int64_t tot = 0;

@@ -82,6 +82,20 @@ int ensure_tmp(mimc3cu_ctx *ctx, BandComm *bc, size_t bytes) {
     return 0;
 }
 
+// CUDA events around a collective on the context stream (only when mimc3cu_comm_timing was switched on)
+struct CommTimer {
+    mimc3cu_ctx *ctx; BandComm *bc; std::vector<std::pair<cudaEvent_t, cudaEvent_t>> *list; cudaEvent_t stop = nullptr;
+    CommTimer(mimc3cu_ctx *c, std::vector<std::pair<cudaEvent_t, cudaEvent_t>> *l) : ctx(c), bc(c->comm), list(l) {
+        if (!bc->timing) return;
+        auto take = [&] { cudaEvent_t e = nullptr; if (!bc->ev_pool.empty()) { e = bc->ev_pool.back(); bc->ev_pool.pop_back(); } else cudaEventCreate(&e); return e; };
+        cudaEvent_t start = take();
+        stop = take();
+        cudaEventRecord(start, ctx->stream);
+        list->push_back({start, stop});
+    }
+    ~CommTimer() { if (stop) cudaEventRecord(stop, ctx->stream); }
+};
+
 }  // namespace
 
 // ---- used by post.cu --------------------------------------------------------------------------------------
@@ -91,6 +105,7 @@ int bandcomm_halo_exchange(mimc3cu_ctx *ctx, void *const *arrays, const int32_t 
     NcclApi *N = nccl_api();
     const bool up = own0 > 0, down = own1 < rows;   // a halo exists <=> a neighbour exists
     if (!up && !down) return 0;
+    CommTimer tm(ctx, &bc->ev_exchange);
     NCCL_CHECK(ctx, N->GroupStart());
     for (int32_t k = 0; k < count; k++) {
         char *base = (char *)arrays[k];
@@ -119,6 +134,7 @@ int bandcomm_halo_or_reduce(mimc3cu_ctx *ctx, uint8_t *flags, int dimx, int rows
     const size_t blk = (size_t)dimx * halo;
     if (int rc = ensure_tmp(ctx, bc, 2 * blk)) return rc;
     uint8_t *from_up = (uint8_t *)bc->tmp, *from_down = from_up + blk;
+    CommTimer tm(ctx, &bc->ev_exchange);
     NCCL_CHECK(ctx, N->GroupStart());
     if (up) {
         NCCL_CHECK(ctx, N->Send(flags + (size_t)dimx * (own0 - halo), blk, ncclChar, bc->rank - 1, (ncclComm_t)bc->comm, ctx->stream));
@@ -140,6 +156,7 @@ int bandcomm_halo_or_reduce(mimc3cu_ctx *ctx, uint8_t *flags, int dimx, int rows
 
 int bandcomm_allreduce_sum(mimc3cu_ctx *ctx, int32_t *dev_vals, int32_t count) {
     BandComm *bc = ctx->comm;
+    CommTimer tm(ctx, &bc->ev_allreduce);
     NCCL_CHECK(ctx, nccl_api()->AllReduce(dev_vals, dev_vals, (size_t)count, ncclInt32, ncclSum, (ncclComm_t)bc->comm, ctx->stream));
     bc->n_allreduce++;
     return 0;
@@ -196,6 +213,8 @@ void mimc3cu_comm_destroy(mimc3cu_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (bc->comm) nccl_api()->CommDestroy((ncclComm_t)bc->comm);
     if (bc->tmp) cudaFree(bc->tmp);
+    for (auto *l : {&bc->ev_exchange, &bc->ev_allreduce}) for (auto &pr : *l) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (auto e : bc->ev_pool) cudaEventDestroy(e);
     delete bc;
     ctx->comm = nullptr;
 }
@@ -206,6 +225,30 @@ int mimc3cu_comm_info(const mimc3cu_ctx *ctx, int32_t *rank, int32_t *world, int
     if (world) *world = ctx->comm->world;
     if (exchanges) *exchanges = ctx->comm->n_exchanges;
     if (allreduces) *allreduces = ctx->comm->n_allreduce;
+    return 0;
+}
+
+// Device time of the collectives since the last call: switches the event bracketing on (on = 1) / off (on = 0) and returns
+// the summed milliseconds of the halo exchanges (incl. the dirty-flag OR) and of the counter all-reduces.  Synchronises.
+int mimc3cu_comm_timing(mimc3cu_ctx *ctx, int32_t on, double *exchange_ms, double *allreduce_ms) {
+    BandComm *bc = ctx->comm;
+    if (!bc) return mimc3cu_fail(ctx, "comm_timing: no communicator");
+    CU_CHECK(ctx, cudaSetDevice(ctx->device));
+    CU_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    double tot[2] = {0.0, 0.0};
+    int k = 0;
+    for (auto *l : {&bc->ev_exchange, &bc->ev_allreduce}) {
+        for (auto &pr : *l) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, pr.first, pr.second) == cudaSuccess) tot[k] += t;
+            bc->ev_pool.push_back(pr.first); bc->ev_pool.push_back(pr.second);
+        }
+        l->clear();
+        k++;
+    }
+    if (exchange_ms) *exchange_ms = tot[0];
+    if (allreduce_ms) *allreduce_ms = tot[1];
+    bc->timing = on != 0;
     return 0;
 }
 

@@ -55,6 +55,11 @@ struct BandComm {
     void *tmp = nullptr;       // receive buffers of the dirty-flag OR-reduction
     size_t tmp_bytes = 0;
     int64_t n_exchanges = 0, n_allreduce = 0;
+    // device time of the collectives (CUDA events around them on the context stream), read by mimc3cu_comm_timing
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_exchange, ev_allreduce;
+    std::vector<cudaEvent_t> ev_pool;
+    double ms_exchange = 0.0, ms_allreduce = 0.0;
+    bool timing = false;
 };
 
 struct mimc3cu_ctx {

@@ -8,10 +8,12 @@
 // reads back one small counter block per sweep.
 //
 // Arithmetic follows the reference's float/double mix operation by operation (this TU is
-// built with -fmad=false).  Two library calls differ from glibc in the last ulp and are
-// the only source of non-bit-equality: expf() in the dpf1 weights (:1514) and exp() in the
-// pseudosmoothing weights (:2157).  Both only influence which cluster is nearest to an
-// interpolated value, i.e. they matter on exact ties only.
+// built with -fmad=false).  Two library calls can differ from glibc in the last ulp and are
+// the only source of non-bit-equality: expf() in the dpf1 weights (:1514; evaluated through the
+// double-precision exp here, which agrees with glibc's expf except for rare double-rounding
+// cases) and exp() in the pseudosmoothing weights (:2157; CUDA 1 ulp vs glibc < 1 ulp).  Both
+// only influence which cluster is nearest to an interpolated value, i.e. they matter on exact
+// ties only.
 #include <math_constants.h>
 
 #include <vector>
@@ -204,7 +206,10 @@ __global__ void __launch_bounds__(kT) dpf1_sweep_kernel(const float *__restrict_
     r2[id_w_max] = 0.0f; r2[id_w_min] = 0.0f;                                   // :1496-1497
     float sum_w = 0.f, sum_w_dp = 0.f, sum_w_dpe = 0.f, sum_noi = 0.f;
     for (int k = 0; k < nn; k++) {
-        float w2 = __fdiv_rn(__fdiv_rn(1.0f, __fadd_rn(1.0f, expf(__fadd_rn(-r5[k], 5.0f)))), 1.0f);   // :1514
+        // expf through the double-precision exp: correctly rounded to float except for one-in-millions double-rounding
+        // cases, like glibc's expf -- CUDA's own expf (2 ulp) made the interpolated fields differ in the last bit
+        const float ex = __double2float_rn(exp((double)__fadd_rn(-r5[k], 5.0f)));
+        float w2 = __fdiv_rn(__fdiv_rn(1.0f, __fadd_rn(1.0f, ex)), 1.0f);   // :1514
         sum_w = __fadd_rn(sum_w, r2[k]);
         sum_w_dp = __fadd_rn(sum_w_dp, __fdiv_rn(__fmul_rn(__fmul_rn(r2[k], w2), r4[k]), r6[k]));
         sum_w_dpe = __fadd_rn(sum_w_dpe, __fdiv_rn(__fmul_rn(__fmul_rn(r2[k], w2), r5[k]), r6[k]));

@@ -61,6 +61,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "mimc3cu_image_download": (C.c_int, [vp, i32, vp]),
         "mimc3cu_image_fill_zero": (C.c_int, [vp, i32]),
         "mimc3cu_image_ptr": (vp, [vp, i32]),
+        "mimc3cu_image_invalidate": (C.c_int, [vp, i32]),
         "mimc3cu_conv2": (C.c_int, [vp, i32, vp, i32, i32, i32]),
         "mimc3cu_get_uv_pivot": (i64, [vp, i32, f32, f32, f32, f32, i32, i32, i32, vp, vp]),
         "mimc3cu_set_nodes": (C.c_int, [vp, vp, i32]),
@@ -91,6 +92,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
         "mimc3cu_comm_destroy": (None, [vp]),
         "mimc3cu_comm_info": (C.c_int, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64), C.POINTER(i64)]),
         "mimc3cu_comm_gather": (C.c_int, [vp, vp, vp, vp, i32]),
+        "mimc3cu_comm_timing": (C.c_int, [vp, i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
         "mimc3cu_dp_negate_uv_async": (C.c_int, [vp, vp, i32]),
         "mimc3cu_set_matcher": (C.c_int, [vp, i32]),
         "mimc3cu_last_matcher": (C.c_int, [vp]),
@@ -118,6 +120,7 @@ EXPORTED_SYMBOLS = (
     "mimc3cu_get_offset_image", "mimc3cu_band_halo", "mimc3cu_postprocess_band", "mimc3cu_image_fill_zero",
     "mimc3cu_multimatch_diag_async", "mimc3cu_comm_unique_id", "mimc3cu_comm_init_rank", "mimc3cu_comm_init_all",
     "mimc3cu_comm_destroy", "mimc3cu_comm_info", "mimc3cu_comm_gather", "mimc3cu_dp_negate_uv_async",
+    "mimc3cu_image_invalidate", "mimc3cu_comm_timing",
 )
 
 
@@ -374,6 +377,12 @@ class Context:
         if self.L.mimc3cu_comm_info(self.h, C.byref(r), C.byref(w), C.byref(e), C.byref(a)):
             return None
         return {"rank": r.value, "world": w.value, "halo_exchanges": e.value, "allreduces": a.value}
+
+    def comm_timing(self, on=True):
+        """(exchange_ms, allreduce_ms): device time of the band collectives since the last call; switches the timing on/off."""
+        a = C.c_double(); b = C.c_double()
+        self._ck(self.L.mimc3cu_comm_timing(self.h, int(on), C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def comm_gather(self, send_dev, bytes_per_rank, recv_dev, root=0):
         b = np.ascontiguousarray(bytes_per_rank, dtype=np.int64)

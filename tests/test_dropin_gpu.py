@@ -64,11 +64,20 @@ def test_unchanged_driver_with_the_cuda_module_writes_the_same_files(tmp_path, d
     assert np.array_equal(vm.vx, a["vx"], equal_nan=True) and np.array_equal(vm.flagcp, a["flagcp"])
     assert vm.meta["cp_offset_int_u"] == sc.offset[0] and vm.meta["name_i0"].endswith("_i0.tif")
     assert a["vx"].shape == (sc.dimy, sc.dimx)
+    report = []
     for k in ("vx", "vy", "ex", "ey", "qual"):
         assert np.array_equal(np.isnan(a[k]), np.isnan(b[k])), k
-        # bit-identical except where glibc/CUDA expf differ by an ulp inside the hole-filling weights
+        # bit-identical except where glibc / CUDA exp differ by an ulp inside the hole-filling and pseudosmoothing weights
+        # (interpolated nodes only); the count is written to gpurun_out/ so that it can be quoted
+        fin = ~np.isnan(a[k])
+        differ = int((a[k] != b[k])[fin].sum())
+        report.append(f"{dtype} {k}: {differ} of {int(fin.sum())} finite values not bit-identical, max |diff| {float(np.nanmax(np.abs(a[k] - b[k]))):.3g}")
         assert np.allclose(a[k], b[k], rtol=1e-5, atol=1e-4, equal_nan=True), (k, np.nanmax(np.abs(a[k] - b[k])))
-        assert (a[k] == b[k])[~np.isnan(a[k])].mean() > 0.98, k
+        assert differ <= 0.005 * fin.sum(), report[-1]
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, f"dropin_bit_identity_{dtype}.txt"), "w") as f:
+            f.write("\n".join(report) + "\n")
     assert abs(float(a["meta"]["cp_offset_subint_u"]) - float(b["meta"]["cp_offset_subint_u"])) < 1e-4
 
 
