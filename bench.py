@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the MIMC3 per-grid-node matching hot path on B200.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2|c1|c4]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload c2|c1|c3|c4|c5|c5s|c5s_small]
 
 Metric (BASELINE.json): grid nodes matched per second.  One node = all 32 matching
 attempts (4 chip sizes x {forward, swapped} x {raw, d/dx, d/dy, Laplacian}) + its share of
@@ -10,24 +10,33 @@ one pass of that path over every node of the workload.
 
   value  device-timed (CUDA events on the library's stream, max over ranks), inputs
          (both images, nodes, pivots) already resident in HBM.
-  e2e    the same metric through the C-ABI host entry points with HOST buffers: pinned
-         u16/u8 images and xyuvav copied H2D, host pivot generation, multi-match,
-         postprocess, finalize, five planes copied D2H -- all inside the timed region.
+  e2e    the same metric through the C-ABI host entry points with HOST buffers, `--steps` timed steps: pinned
+         u16/u8 images and xyuvav copied H2D, the control-point stage (N = 1), host pivot generation,
+         multi-match, postprocess, finalize, five planes copied D2H -- all inside the timed region.
   roofline      dominant kernel = the matcher (match2_kernel<ocw,G>, plus match_kernel for nodes
                 outside its class); achieved = sum over attempts and nodes of 8*S^2*E flop
                 (E = NCC cells the reference algorithm evaluates, counted by the kernel and
                 cross-checked against the oracle in tests) / summed matcher durations (CUDA
                 events recorded by the library around every attempt inside the timed
                 region); peak = FP32 FMA throughput measured live by an FMA micro-benchmark
-                (MEASURED_PEAKS.json has no FP32 CUDA-core figure).
+                (MEASURED_PEAKS.json has no FP32 CUDA-core figure); peak_nominal / frac_nominal =
+                the same against 148 SMs x 128 lanes x 2 x the maximum SM clock.
   cpu_baseline  the UNMODIFIED reference (oracle/_ref/libmimc3ref.so, OpenMP, all host
-                threads) on a bounded node sample of the same workload.
+                threads) on a bounded sample of the same workload: 32 attempts on four node rows of the
+                full images, the six conv2 calls on the full images, the control-point stage once.
+  parity        (N = 1) the GPU results of the measured scene against that reference sample (dp of all 32
+                attempts bit for bit), against the oracle (integer peaks, evaluated cells) and the postprocess of
+                a band of node rows against the oracle's (cluster choice): mismatch counts.
+  --impl reference   the same CPU sample as its own arm (rank 0 alone under torchrun); loads nothing of
+                libmimc3cu.so.
 
-N > 1 (torchrun): weak scaling.  Every rank owns one tile of a vertical mosaic (its own
+N > 1 (torchrun), default workloads: weak scaling.  Every rank owns one tile of a vertical mosaic (its own
 image pair + node-row band) and matches it with no data-path collective.  The postprocess
-runs banded over the whole mosaic grid: each rank sweeps its own band and exchanges halo
-rows / dirty flags / sweep counters with its neighbours over NCCL (mimc3_b200/bands.py),
-then the five planes are gathered on rank 0.  Timing = max over ranks.
+runs banded over the whole mosaic grid: each rank sweeps its own band; halo rows, dirty flags and sweep counters
+travel over NCCL, issued by the library itself on its stream (csrc/comm.cu; `--band-comm python` routes them
+through the callbacks of mimc3_b200/bands.py instead), then the five planes are gathered on rank 0.
+`--workload c5s`: strong scaling -- ONE 32768^2 scene, node-row bands (balanced by pivot counts) over the ranks.
+Timing = max over ranks.
 """
 from __future__ import annotations
 

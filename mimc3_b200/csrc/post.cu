@@ -55,6 +55,7 @@ struct Post {
     uint8_t *stack = nullptr;   // (kMaxStack, n)
     int32_t *ruv = nullptr;     // (MAXNB, 2)
     int32_t *ctr = nullptr;     // device counters (256 ints)
+    int32_t *list[2] = {nullptr, nullptr};   // work lists of the sweeps (local node indices): holes still to fill / dirty nodes
     double *apv = nullptr;      // (n, 2) a-priori vx, vy (xyuvav cols 4,5)
     size_t cap_n = 0;
     int32_t stack_cap = 0;
@@ -161,11 +162,13 @@ __global__ void __launch_bounds__(kT) dpf1_sweep_kernel(const float *__restrict_
                                                         float *__restrict__ dxb, float *__restrict__ dyb, float *noi,
                                                         const int *__restrict__ ncl, const double *__restrict__ apv,
                                                         const int *__restrict__ ruv, int nruv, const Band B,
-                                                        float factor, int thres_n, float thres_weight, int *ctr) {
+                                                        float factor, int thres_n, float thres_weight, int *ctr,
+                                                        const int *__restrict__ list, const int *__restrict__ list_len) {
     const int dimx = B.dimx, dimy = B.rows;
-    int g = blockIdx.x * kT + threadIdx.x;
-    if (g >= dimx * (B.own1 - B.own0)) return;
-    g += B.own0 * dimx;
+    // the holes still to fill are kept as a list (dense warps: a thread per grid node left one lane in thirty busy)
+    const int i = blockIdx.x * kT + threadIdx.x;
+    if (i >= *list_len) return;
+    const int g = list[i];
     if (!(isnan(__fadd_rn(dx[g], dy[g])) && ncl[g] != 0)) return;               // :1412
     const int cv = g / dimx, cu = g - cv * dimx;
     float dpe0 = __double2float_rn(__dmul_rn(apv[2 * (size_t)g], (double)factor));
@@ -227,14 +230,33 @@ __global__ void __launch_bounds__(kT) dpf1_sweep_kernel(const float *__restrict_
     }
 }
 
-// Jacobi commit :1577-1589 + count of still-unprocessed nodes :1600-1611
-__global__ void __launch_bounds__(kT) dpf1_commit_kernel(float *dx, float *dy, float *dxb, float *dyb, const int *ncl, int n,
-                                                         int *ctr) {
-    int g = blockIdx.x * kT + threadIdx.x;
-    if (g >= n) return;
+// Jacobi commit :1577-1589 + count of still-unprocessed nodes :1600-1611, over the hole list; the holes that remain
+// form the next list (its order does not matter: the sweep is a Jacobi iteration)
+__global__ void __launch_bounds__(kT) dpf1_commit_kernel(float *dx, float *dy, float *dxb, float *dyb, const int *ncl,
+                                                         const int *__restrict__ list, const int *__restrict__ list_len,
+                                                         int *__restrict__ next_list, int *next_len, int *ctr) {
+    const int i = blockIdx.x * kT + threadIdx.x;
+    if (i >= *list_len) return;
+    const int g = list[i];
     float a = dxb[g], b = dyb[g];
     if (!isnan(a) && !isnan(b)) { dx[g] = a; dy[g] = b; dxb[g] = CUDART_NAN_F; dyb[g] = CUDART_NAN_F; }
-    if ((isnan(dx[g]) || isnan(dy[g])) && ncl[g] != 0) atomicAdd(&ctr[1], 1);
+    if ((isnan(dx[g]) || isnan(dy[g])) && ncl[g] != 0) {
+        atomicAdd(&ctr[1], 1);
+        next_list[atomicAdd(next_len, 1)] = g;
+    }
+}
+
+// Work list of a sweep: the (local) indices of the owned nodes with flag[g] != 0 / of the holes left by get_dpf0.
+__global__ void __launch_bounds__(kT) list_flagged_kernel(const uint8_t *__restrict__ flag, int first, int n, int *__restrict__ list, int *len) {
+    const int g = first + blockIdx.x * kT + threadIdx.x;
+    if (g >= first + n) return;
+    if (flag[g]) list[atomicAdd(len, 1)] = g;
+}
+__global__ void __launch_bounds__(kT) list_holes_kernel(const float *__restrict__ dx, const float *__restrict__ dy, const int *__restrict__ ncl,
+                                                        int first, int n, int *__restrict__ list, int *len) {
+    const int g = first + blockIdx.x * kT + threadIdx.x;
+    if (g >= first + n) return;
+    if ((isnan(dx[g]) || isnan(dy[g])) && ncl[g] != 0) list[atomicAdd(len, 1)] = g;
 }
 
 // 3x3 box smoothing of the filled nodes :1623-1666 (reads dx/dy, writes dxb/dyb for interior nodes)
@@ -326,11 +348,12 @@ __global__ void __launch_bounds__(kT) ps_sweep_kernel(const uint8_t *__restrict_
                                                       const float *__restrict__ dx, const float *__restrict__ dy,
                                                       float *bx, float *by, int *bid, const float *__restrict__ mvn,
                                                       const int *__restrict__ ncl, int K, const double *__restrict__ apv,
-                                                      const int *__restrict__ ruv, int nruv, const Band B, int *ctr) {
+                                                      const int *__restrict__ ruv, int nruv, const Band B, int *ctr,
+                                                      const int *__restrict__ list, const int *__restrict__ list_len) {
     const int dimx = B.dimx, dimy = B.rows;
-    int g = blockIdx.x * kT + threadIdx.x;
-    if (g >= dimx * (B.own1 - B.own0)) return;
-    g += B.own0 * dimx;
+    const int i = blockIdx.x * kT + threadIdx.x;   // a thread per dirty node of the list (dense warps)
+    if (i >= *list_len) return;
+    const int g = list[i];
     if (!mask[g]) return;
     const int cv = g / dimx, cu = g - cv * dimx;
     signed char nu[MAXNB], nv[MAXNB];
@@ -471,6 +494,7 @@ int post_alloc(mimc3cu_ctx *ctx, int32_t n, int32_t K) {
     CU_CHECK(ctx, cudaMalloc(&Q.mask[0], N)); CU_CHECK(ctx, cudaMalloc(&Q.mask[1], N));
     CU_CHECK(ctx, cudaMalloc(&Q.ruv, MAXNB * 2 * sizeof(int32_t)));
     CU_CHECK(ctx, cudaMalloc(&Q.ctr, 256 * sizeof(int32_t)));
+    CU_CHECK(ctx, cudaMalloc(&Q.list[0], N * 4)); CU_CHECK(ctx, cudaMalloc(&Q.list[1], N * 4));
     CU_CHECK(ctx, cudaMalloc(&Q.apv, N * 2 * sizeof(double)));
     Q.cap_n = N; Q.n = n; Q.K = K;
     return 0;
@@ -507,7 +531,7 @@ void post_free(mimc3cu_ctx *ctx) {
     Post &P = *ctx->post;
     for (void *p : {(void *)P.mvn, (void *)P.ncl, (void *)P.dpf0, (void *)P.id, (void *)P.id1, (void *)P.bid, (void *)P.dx,
                     (void *)P.dy, (void *)P.dxb, (void *)P.dyb, (void *)P.noi, (void *)P.dx1, (void *)P.dy1, (void *)P.mask[0],
-                    (void *)P.mask[1], (void *)P.stack, (void *)P.ruv, (void *)P.ctr, (void *)P.apv})
+                    (void *)P.mask[1], (void *)P.stack, (void *)P.ruv, (void *)P.ctr, (void *)P.apv, (void *)P.list[0], (void *)P.list[1]})
         if (p) cudaFree(p);
     delete ctx->post;
     ctx->post = nullptr;
@@ -605,6 +629,16 @@ int post_run_band(mimc3cu_ctx *ctx, const float *dp, const double *xyuvav, const
     for (int k = 0; k < nruv; k++) if (abs(ruv[2 * k + 1]) > halo) return mimc3cu_fail(ctx, "postprocess: neighbour offset beyond the halo");
     CU_CHECK(ctx, cudaMemcpyAsync(P.ruv, ruv.data(), sizeof(int32_t) * 2 * (size_t)nruv, cudaMemcpyHostToDevice, st));
     const float factor = (float)(1.0 / 365.0 * (double)p->dt / (double)p->mpp);   // :1393
+    // the sweeps work on the list of holes: ctr[200 + k] is the length of list[k]
+    int cur = 0;
+    CU_CHECK(ctx, cudaMemsetAsync(P.ctr + 200, 0, 2 * sizeof(int32_t), st));
+    list_holes_kernel<<<nb, kT, 0, st>>>(P.dx, P.dy, P.ncl, off, n, P.list[0], P.ctr + 200);
+    ctx->launches++;
+    // own holes of this band: sizes the sweep launches (the list only shrinks)
+    int32_t own_holes = 0;
+    CU_CHECK(ctx, cudaMemcpyAsync(&own_holes, P.ctr + 200, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CU_CHECK(ctx, cudaStreamSynchronize(st));
+    const int nbh = std::max(1, nblocks((size_t)own_holes));
     int32_t NOI = 0, unprocessed = 1;
     for (int thres_n = nruv - 1; thres_n >= 3; thres_n--) {
         float thres_weight = 0.5f;
@@ -614,9 +648,12 @@ int post_run_band(mimc3cu_ctx *ctx, const float *dp, const double *xyuvav, const
             while (processed != 0) {
                 NOI++;
                 CU_CHECK(ctx, cudaMemsetAsync(P.ctr, 0, 2 * sizeof(int32_t), st));
-                dpf1_sweep_kernel<<<nb, kT, 0, st>>>(P.dx, P.dy, P.dxb, P.dyb, P.noi, P.ncl, P.apv, P.ruv, nruv, B, factor,
-                                                     thres_n, thres_weight, P.ctr);
-                dpf1_commit_kernel<<<nb, kT, 0, st>>>(P.dx + off, P.dy + off, P.dxb + off, P.dyb + off, P.ncl + off, n, P.ctr);
+                CU_CHECK(ctx, cudaMemsetAsync(P.ctr + 200 + (cur ^ 1), 0, sizeof(int32_t), st));
+                dpf1_sweep_kernel<<<nbh, kT, 0, st>>>(P.dx, P.dy, P.dxb, P.dyb, P.noi, P.ncl, P.apv, P.ruv, nruv, B, factor,
+                                                      thres_n, thres_weight, P.ctr, P.list[cur], P.ctr + 200 + cur);
+                dpf1_commit_kernel<<<nbh, kT, 0, st>>>(P.dx, P.dy, P.dxb, P.dyb, P.ncl, P.list[cur], P.ctr + 200 + cur, P.list[cur ^ 1],
+                                                       P.ctr + 200 + (cur ^ 1), P.ctr);
+                cur ^= 1;
                 ctx->launches += 2;
                 if (int rc = read_counters(h_ctr, 2)) return rc;
                 processed = h_ctr[0];
@@ -654,8 +691,13 @@ int post_run_band(mimc3cu_ctx *ctx, const float *dp, const double *xyuvav, const
         if (int rc = ensure_stack(ctx, nstack + 1)) return rc;
         CU_CHECK(ctx, cudaMemsetAsync(next, 0, (size_t)nl, st));
         CU_CHECK(ctx, cudaMemsetAsync(P.ctr, 0, 128 * sizeof(int32_t), st));
+        // the dirty nodes of this sweep as a list (ctr[200] = its length); a dirty node does a 6x6 weighted least-squares fit
+        // over up to 81 neighbours, so dense warps matter
+        CU_CHECK(ctx, cudaMemsetAsync(P.ctr + 200, 0, sizeof(int32_t), st));
+        list_flagged_kernel<<<nb, kT, 0, st>>>(mask, off, n, P.list[0], P.ctr + 200);
         ps_sweep_kernel<<<nb, kT, 0, st>>>(mask, next, P.stack, P.id, P.dx, P.dy, P.dxb, P.dyb, P.bid, P.mvn, P.ncl, K, P.apv, P.ruv,
-                                           nruv, B, P.ctr);
+                                           nruv, B, P.ctr, P.list[0], P.ctr + 200);
+        ctx->launches++;
         ps_commit_kernel<<<nb, kT, 0, st>>>(P.dx + off, P.dy + off, P.id + off, P.dxb + off, P.dyb + off, P.bid + off, n);
         ctx->launches += 2;
         if (nccl) {                   // dirty flags scattered into the neighbours' rows: OR them into their owners
