@@ -138,30 +138,34 @@ struct Cfg {
     // 16-byte staging loads where the register budget has room for them (measured: +5 % at chip half-width 15; the
     // 64- and 80-register instantiations of the other sizes spill with them and lose 2-13 %)
     static constexpr bool VEC = OCW == 15;
+    // chip pixels straight from global memory into registers instead of through the shared-memory tile: pays for the
+    // smallest chip only (+7 % at half-width 7; the row-per-lane pattern is uncoalesced and costs 10-20 % at 30 / 40,
+    // even when the warps that idle during the previous node's replay do the loading)
+    static constexpr bool DIRECT_CHIP = OCW == 7 && G == 32;
     static_assert(NSEG >= 1, "group too small for this chip");
     static_assert((L + 1) / 2 <= 16, "at most 16 pixels per FP32 accumulator");
 };
 
 // Copies `rows` x `width` floats (global row stride `gstride`) into a shared tile with row pitch
 // `spitch` (columns [width, spitch) are zero-filled), NT threads, thread index `tix`.  Loads are
-// issued eight at a time before the first store: staging is latency-bound, not bandwidth-bound.
-template <int NT>
+// issued DEPTH at a time before the first store: staging is latency-bound, not bandwidth-bound.
+template <int NT, int DEPTH>
 __device__ __forceinline__ void stage_rows(const float *__restrict__ src, int gstride, float *dst, int spitch, int rows, int width,
                                            int tix) {
     const int total = rows * spitch;
     int y = tix / spitch, x = tix - y * spitch;
     const int dy = NT / spitch, dx = NT - dy * spitch;
-    for (int e = tix; e < total; e += NT * 8) {
-        float v[8];
+    for (int e = tix; e < total; e += NT * DEPTH) {
+        float v[DEPTH];
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
+        for (int u = 0; u < DEPTH; u++) {
             const bool ok = e + u * NT < total && x < width;
             v[u] = ok ? __ldg(src + (size_t)y * gstride + x) : 0.0f;
             x += dx; y += dy;
             if (x >= spitch) { x -= spitch; y++; }
         }
 #pragma unroll
-        for (int u = 0; u < 8; u++)
+        for (int u = 0; u < DEPTH; u++)
             if (e + u * NT < total) dst[e + u * NT] = v[u];
     }
 }
@@ -295,6 +299,31 @@ __device__ void subpixel_fit(const float n9[9], int peak_du, int peak_dv, float 
     fv = __double2float_rn(__ddiv_rn((double)fv, det));
     du = __fadd_rn(fu, (float)peak_du);
     dv = __fadd_rn(fv, (float)peak_dv);
+}
+
+// The thread's slice of the reference chip (extract_refchip, MIMC_module.c:845-855: no bounds check there; zero outside
+// the image here) straight from global memory into registers: rows r, r + RPT, ... of column segment col0, `len` pixels
+// each.  A lane per chip row is an uncoalesced pattern, but all loads of the slice are in flight at once, nothing goes
+// through shared memory (the search area can be staged at the same time).  Used where Cfg::DIRECT_CHIP says it pays.
+template <int OCW, int G>
+__device__ __forceinline__ void load_chip_direct(const Match2Args &a, int u0, int v0, int r, int col0, int len,
+                                                 float (&chip)[Cfg<OCW, G>::RB][Cfg<OCW, G>::L]) {
+    using C = Cfg<OCW, G>;
+    constexpr int S = C::S, L = C::L;
+    const bool inside = u0 - OCW >= 0 && v0 - OCW >= 0 && u0 + OCW < a.W && v0 + OCW < a.H;
+#pragma unroll
+    for (int rb = 0; rb < C::RB; rb++) {
+        const int row = r + rb * C::RPT;
+        const int iv = v0 - OCW + row;
+        const float *src = a.ref + (size_t)min(max(iv, 0), a.H - 1) * a.W + (u0 - OCW + col0);
+        const bool rowok = row < S && (inside || (iv >= 0 && iv < a.H));
+#pragma unroll
+        for (int c = 0; c < L; c++) {
+            const int iu = u0 - OCW + col0 + c;
+            const bool ok = rowok && c < len && (inside || (iu >= 0 && iu < a.W));
+            chip[rb][c] = ok ? __ldg(src + c) : 0.0f;
+        }
+    }
 }
 
 // Per-group control block in shared memory.
@@ -703,6 +732,7 @@ __global__ void __launch_bounds__(Cfg<OCW, G>::CTA, MINCTA) match2_kernel(const 
     const int W1 = a.W + 1;
 
     if (t == 0) { ctl.node[0] = atomicAdd(a.counter, 1u); ctl.nslow = 0; }
+    float chip[C::RB][L];        // this thread's chip pixels, in registers for the whole node
     for (int iter = 0;; iter++) {
         gsync<G>();
         const unsigned int idx = ctl.node[iter & 1];
@@ -763,15 +793,16 @@ __global__ void __launch_bounds__(Cfg<OCW, G>::CTA, MINCTA) match2_kernel(const 
             ctl.wstart[i] = st; ctl.wpos[i] = st; ctl.wmax[i] = -2.0f;
         }
 
-        // ---- stage the chip through shared memory into registers (extract_refchip :845-855) ----
-        // 16-byte loads need a row stride of whole float4s and must not reach before / behind the image buffer
-        const bool vec_ok = (a.W & 3) == 0;
-        if (u0 - OCW >= 0 && v0 - OCW >= 0 && u0 + OCW < a.W && v0 + OCW < a.H) {
+        // ---- the chip (extract_refchip :845-855): into registers, straight from global memory or through the shared tile ----
+        const bool vec_ok = (a.W & 3) == 0;   // 16-byte loads need a row stride of whole float4s
+        if (C::DIRECT_CHIP) {
+            load_chip_direct<OCW, G>(a, u0, v0, r, col0, len, chip);
+        } else if (u0 - OCW >= 0 && v0 - OCW >= 0 && u0 + OCW < a.W && v0 + OCW < a.H) {
             const size_t first = (size_t)(v0 - OCW) * a.W + (u0 - OCW);
             if (C::VEC && vec_ok && first >= 3 && first + (size_t)(S - 1) * a.W + S + 3 <= (size_t)a.H * a.W)
                 stage_rows_v4<G, 4>(a.ref + first, a.W, sa, S, S, S, t);
             else
-                stage_rows<G>(a.ref + first, a.W, sa, S, S, S, t);
+                stage_rows<G, 8>(a.ref + first, a.W, sa, S, S, S, t);
         } else {
             for (int i = t; i < S * S; i += G) {
                 const int rr = i / S, cc = i - rr * S;
@@ -792,21 +823,22 @@ __global__ void __launch_bounds__(Cfg<OCW, G>::CTA, MINCTA) match2_kernel(const 
             }
             if (lane >= 2 && lane <= 4) { ctl.chip_ss[lane - 1] = ss; ctl.chip_s[lane - 1] = s; }
         }
-        gsync<G>();
-        if (!ctl.valid) {
-            if (t == 0) {
-                a.dp[3 * (size_t)g] = CUDART_NAN_F; a.dp[3 * (size_t)g + 1] = CUDART_NAN_F; a.dp[3 * (size_t)g + 2] = -3.0f;
-                if (a.peak) a.peak[g] = make_int2(0, 0);
-                if (a.ncell) a.ncell[g] = 0;
+        if (!C::DIRECT_CHIP) {
+            gsync<G>();
+            if (!ctl.valid) {
+                if (t == 0) {
+                    a.dp[3 * (size_t)g] = CUDART_NAN_F; a.dp[3 * (size_t)g + 1] = CUDART_NAN_F; a.dp[3 * (size_t)g + 2] = -3.0f;
+                    if (a.peak) a.peak[g] = make_int2(0, 0);
+                    if (a.ncell) a.ncell[g] = 0;
+                }
+                continue;
             }
-            continue;
+#pragma unroll
+            for (int rb = 0; rb < C::RB; rb++)
+#pragma unroll
+                for (int c = 0; c < L; c++) chip[rb][c] = (c < len && r + rb * C::RPT < S) ? sa[(r + rb * C::RPT) * S + col0 + c] : 0.0f;
+            gsync<G>();
         }
-        float chip[C::RB][L];
-#pragma unroll
-        for (int rb = 0; rb < C::RB; rb++)
-#pragma unroll
-            for (int c = 0; c < L; c++) chip[rb][c] = (c < len && r + rb * C::RPT < S) ? sa[(r + rb * C::RPT) * S + col0 + c] : 0.0f;
-        gsync<G>();
 
         // ---- stage the search area (extract_sarea :857-890): zero outside the image, zero in the
         //      never-written last row / column, zero in the pad columns [Dx2, pitch) ----------------
@@ -816,7 +848,7 @@ __global__ void __launch_bounds__(Cfg<OCW, G>::CTA, MINCTA) match2_kernel(const 
             if (C::VEC && vec_ok && first >= 3 && first + (size_t)(Dy2 - 2) * a.W + Dx2 + 2 <= (size_t)a.H * a.W)
                 stage_rows_v4<G, (G >= 128 ? 2 : 4)>(a.srch + first, a.W, sa, pitch, Dy2 - 1, Dx2 - 1, t);   // the chip pixels are live here: fewer loads in flight
             else
-                stage_rows<G>(a.srch + first, a.W, sa, pitch, Dy2 - 1, Dx2 - 1, t);
+                stage_rows<G, 8>(a.srch + first, a.W, sa, pitch, Dy2 - 1, Dx2 - 1, t);
             for (int x = t; x < pitch; x += G) sa[(Dy2 - 1) * pitch + x] = 0.0f;
         } else {
             for (int y = gwarp; y < Dy2; y += C::NWARPS) {
@@ -837,6 +869,14 @@ __global__ void __launch_bounds__(Cfg<OCW, G>::CTA, MINCTA) match2_kernel(const 
             ctl.m = 0; ctl.nblk = 0;
         }
         gsync<G>();
+        if (!ctl.valid) {   // investigate_valid_grid: the search area was staged for nothing (rare)
+            if (t == 0) {
+                a.dp[3 * (size_t)g] = CUDART_NAN_F; a.dp[3 * (size_t)g + 1] = CUDART_NAN_F; a.dp[3 * (size_t)g + 2] = -3.0f;
+                if (a.peak) a.peak[g] = make_int2(0, 0);
+                if (a.ncell) a.ncell[g] = 0;
+            }
+            continue;
+        }
         PROF_T(t_stage1);
         PROF_ADD(1, t_stage1 - t_node0);
         // this thread's view of the tile: row r, first column col0 (threads without chip pixels: the origin)
