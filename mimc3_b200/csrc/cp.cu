@@ -42,6 +42,24 @@ __global__ void __launch_bounds__(kT) cp_nullcount_kernel(const float *__restric
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(&count[g], c);
 }
 
+// The same count from the image's summed-area table (sat.cu: the low 24 bits of .y count the pixels < 1e-10).  For an
+// exact-class image (non-negative multiples of 1/8) "< 0.00001" and "< 1e-10" both mean "== 0", so the counts agree;
+// one thread per node instead of one CTA: the candidate list is most of the grid (16 M nodes at 8-px spacing).
+__global__ void __launch_bounds__(kT) cp_nullcount_sat_kernel(const ulonglong2 *__restrict__ sat, int H, int W, const int2 *__restrict__ uv,
+                                                              int n, int ocw, int *__restrict__ count) {
+    const int g = blockIdx.x * kT + threadIdx.x;
+    if (g >= n) return;
+    const int x0 = max(uv[g].x - ocw, 0), y0 = max(uv[g].y - ocw, 0), x1 = min(uv[g].x + ocw + 1, W), y1 = min(uv[g].y + ocw + 1, H);
+    int c = 0;
+    if (x1 > x0 && y1 > y0) {
+        const size_t W1 = (size_t)W + 1;
+        const unsigned long long a = __ldg(&sat[y1 * W1 + x1]).y, b = __ldg(&sat[y0 * W1 + x1]).y;
+        const unsigned long long cc = __ldg(&sat[y1 * W1 + x0]).y, d = __ldg(&sat[y0 * W1 + x0]).y;
+        c = (int)((a - b - cc + d) & 0xffffffull);
+    }
+    count[g] = c;
+}
+
 __device__ __forceinline__ float px_or_zero(const float *img, int H, int W, int y, int x) {
     return (x >= 0 && x < W && y >= 0 && y < H) ? __ldg(&img[(size_t)y * W + x]) : 0.0f;
 }
@@ -169,7 +187,13 @@ int cp_get_offset_image(mimc3cu_ctx *ctx, Image *i0, Image *i1, const double *xy
         CU_CHECK(ctx, d_cnt.alloc(sizeof(int) * uv.size()));
         CU_CHECK(ctx, cudaMemcpyAsync(d_uv.p, uv.data(), sizeof(int2) * uv.size(), cudaMemcpyHostToDevice, st));
         CU_CHECK(ctx, cudaMemsetAsync(d_cnt.p, 0, sizeof(int) * uv.size(), st));
-        cp_nullcount_kernel<<<(unsigned)uv.size(), kT, 0, st>>>(i0->d, H, W, d_uv.as<int2>(), (int)uv.size(), ocw2, d_cnt.as<int>());
+        // the table is needed by the matcher anyway (raw-pair attempts) and is cached with the image
+        if (ctx->matcher != 1) { if (int rc = ensure_image_sat(ctx, i0)) return rc; }
+        if (ctx->matcher != 1 && i0->exact_class && i0->sat_valid)
+            cp_nullcount_sat_kernel<<<(unsigned)((uv.size() + kT - 1) / kT), kT, 0, st>>>((const ulonglong2 *)i0->sat, H, W, d_uv.as<int2>(),
+                                                                                      (int)uv.size(), ocw2, d_cnt.as<int>());
+        else
+            cp_nullcount_kernel<<<(unsigned)uv.size(), kT, 0, st>>>(i0->d, H, W, d_uv.as<int2>(), (int)uv.size(), ocw2, d_cnt.as<int>());
         ctx->launches++;
         CU_CHECK(ctx, cudaGetLastError());
         std::vector<int> cnt(uv.size());

@@ -925,21 +925,23 @@ inline int bin_table(int ocw, BinCfg *t) {
     // (measured: 8 nodes per SM at 64 registers spill and lose 20 %), then whole CTAs for the wide search areas
     if (ocw == 30) { t[0] = {128, 2, 3}; t[1] = {128, 2, 2}; t[2] = {256, 1, 2}; t[3] = {256, 1, 1}; return 4; }
     if (ocw >= 30) { t[0] = {256, 1, 4}; t[1] = {128, 1, 3}; t[2] = {256, 1, 2}; t[3] = {256, 1, 1}; return 4; }
-    // small chips: a warp per node while eight nodes (one CTA) fit on an SM; nodes with very wide search
-    // areas (fast ice) would leave the SM with one or two warps that way, so they get a whole
+    // small chips: a warp per node, eight nodes per CTA, as many CTAs per SM as the nodes' search areas allow; nodes with
+    // very wide search areas (fast ice) would leave the SM with one or two warps that way, so they get a whole
     // 256-thread CTA each (row segments of <= 4 pixels per thread): more instructions per cell, but
     // many more resident warps (measured: +10 % on the fast-glacier workload, a loss for moderate areas)
-    t[0] = {32, 8, ocw == 7 ? 4 : 2}; t[1] = {32, 8, 2}; t[2] = {32, 8, 1}; t[3] = {256, 1, 3}; t[4] = {256, 1, 1};
+    if (ocw == 7) { t[0] = {32, 8, 4}; t[1] = {32, 8, 3}; t[2] = {32, 8, 2}; t[3] = {256, 1, 3}; t[4] = {256, 1, 1}; }
+    // half-width 15: between two CTAs of eight nodes and one CTA of eight nodes, two CTAs of five nodes (ten warps per SM)
+    else { t[0] = {32, 8, 2}; t[1] = {32, 5, 2}; t[2] = {32, 8, 1}; t[3] = {256, 1, 3}; t[4] = {256, 1, 1}; }
     return 5;
 }
-// Development aid: MIMC3CU_BINS="40:128,1,5;30:64,4,2" replaces the FIRST bin of the named chip half-widths
+// Development aid: MIMC3CU_BINS="40:0:128,1,5;30:1:256,1,3" replaces bin <index> of the named chip half-widths
 // (only combinations with a compiled instantiation: see the dispatch in launch_match2).
 inline int bin_table_env(int ocw, BinCfg *t) {
     const int nb = bin_table(ocw, t);
     if (const char *e = getenv("MIMC3CU_BINS")) {
         for (const char *p = e; p && *p;) {
-            int o = 0, G = 0, groups = 0, ctas = 0;
-            if (sscanf(p, "%d:%d,%d,%d", &o, &G, &groups, &ctas) == 4 && o == ocw) t[0] = {G, groups, ctas};
+            int o = 0, idx = 0, G = 0, groups = 0, ctas = 0;
+            if (sscanf(p, "%d:%d:%d,%d,%d", &o, &idx, &G, &groups, &ctas) == 5 && o == ocw && idx >= 0 && idx < nb) t[idx] = {G, groups, ctas};
             p = strchr(p, ';');
             if (p) p++;
         }
