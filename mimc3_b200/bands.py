@@ -46,9 +46,11 @@ def split_rows(dimy: int, world: int, min_rows: int = 1, weights=None):
 def row_work(csr_offsets, dimx: int, dimy: int) -> np.ndarray:
     """Matching cost estimate per node row, known before any matching: a node-attempt evaluates about
     3 * (P + 2) correlation cells for P DLC pivots, so fast-glacier rows are several times
-    dearer than static ones; on top of the cells every node-attempt has a fixed cost (staging, the serial
-    replay) worth about ten pivots (cycle counters of the matcher, profiles/): weight P + 12.  With P + 2 the
-    slow-ice bands of the 8-GPU run of one scene finished 7 % after the fast-ice bands.
+    dearer than static ones.  The weight is P itself, calibrated on the 8-GPU run of one 32768^2 scene
+    (profiles/): every node-attempt also has a fixed cost (staging, the serial replay), which argues for P + c
+    with c > 0, but nodes with long pivot lines run in the less efficient wide-search-area bins and need more
+    evaluation rounds, which outweighs it -- with P + 2 / P + 5 / P + 12 the fast-ice bands finished
+    7 / 10 / 15 % after the slow-ice ones.
     ``csr_offsets``: one int array (n + 1) per chip size, as get_uv_pivot returns them.  Feed the result to
     ``split_rows(weights=...)``."""
     w = np.zeros(dimy, np.float64)
@@ -56,7 +58,7 @@ def row_work(csr_offsets, dimx: int, dimy: int) -> np.ndarray:
         P = np.diff(np.asarray(off, dtype=np.int64))
         if P.shape[0] != dimx * dimy:
             raise ValueError(f"{P.shape[0]} nodes do not form a {dimy} x {dimx} grid")
-        w += (P + 12).reshape(dimy, dimx).sum(axis=1)
+        w += P.reshape(dimy, dimx).sum(axis=1)
     return w
 
 

@@ -194,8 +194,8 @@ void drop_run_state() {
     for (auto &D : g_devs) D.nodes_set = false;
 }
 
-// Bands of node rows, one per GPU, balanced by the matching cost of the rows (sum of P + 12 over the row's nodes:
-// a node-attempt evaluates about 3 (P + 2) cells and has a fixed cost worth about ten pivots, cf. bands.row_work);
+// Bands of node rows, one per GPU, balanced by the matching cost of the rows (sum of P over the row's nodes;
+// calibrated on the 8-GPU run of one scene, see bands.row_work);
 // every band keeps at least `halo` rows for the banded postprocess.
 void assign_bands(const double *xy, int32_t n, const std::vector<int32_t> *off) {
     const int nd = (int)g_devs.size();
@@ -211,7 +211,7 @@ void assign_bands(const double *xy, int32_t n, const std::vector<int32_t> *off) 
     std::vector<double> cum((size_t)g_dimy + 1, 0.0);
     for (int32_t r = 0; r < g_dimy; r++) {
         double w = g_dimx;
-        if (off) w = (double)((*off)[(size_t)(r + 1) * g_dimx] - (*off)[(size_t)r * g_dimx]) + 12.0 * g_dimx;
+        if (off) w = (double)((*off)[(size_t)(r + 1) * g_dimx] - (*off)[(size_t)r * g_dimx]);
         cum[r + 1] = cum[r] + w;
     }
     int32_t prev = 0;

@@ -25,7 +25,7 @@ for name, binary in (("reference (OpenMP)", oracle.REF_CLI), ("CUDA drop-in", os
     r = subprocess.run([binary, os.path.join(work, "20200101000000_i0.tif"), os.path.join(work, "20200117000000_i1.tif"),
                         os.path.join(work, "xyuvav.GMA"), out], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     dt = time.perf_counter() - t0
-    match = sum(float(l.split(":")[1].split()[0]) for l in r.stdout.splitlines() if l.startswith("Elapsed time"))
+    match = sum(float(l.split("Elapsed time:")[1].split()[0]) for l in r.stdout.splitlines() if "Elapsed time:" in l)
     res[name] = (dt, match, out)
     print(f"{name:20s} rc={r.returncode} wall {dt:7.2f} s   sum of the driver's own 'Elapsed time' prints around matching_ncc_dlc_2: {match:7.2f} s   ({sc.n} nodes, {os.cpu_count()} host cores)")
 a = synth.read_gma(os.path.join(res["reference (OpenMP)"][2], "vmap_20200101000000_20200117000000_vx.GMA"))

@@ -44,7 +44,7 @@ for name, binary, extra in runs:
     r = subprocess.run([binary, os.path.join(work, "20200101000000_i0.tif"), os.path.join(work, "20200117000000_i1.tif"),
                         os.path.join(work, "xyuvav.GMA"), out], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     wall = time.perf_counter() - t0
-    match = sum(float(l.split(":")[1].split()[0]) for l in r.stdout.splitlines() if l.startswith("Elapsed time"))
+    match = sum(float(l.split("Elapsed time:")[1].split()[0]) for l in r.stdout.splitlines() if "Elapsed time:" in l)
     print(f"{name:20s} rc={r.returncode} wall {wall:8.2f} s; the driver's own 'Elapsed time' prints around matching_ncc_dlc_2 sum to {match:8.2f} s "
           f"({os.cpu_count()} host cores, {args.devices} GPU(s))")
     if r.returncode:
