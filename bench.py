@@ -605,7 +605,7 @@ def main():
                "h2d_bytes_per_step": int(world * (i0_host.nbytes + i1_host.nbytes) + 6 * 8 * n_total + world * pl.pivot_bytes),
                "d2h_bytes_per_step": int(5 * 4 * n_total), "ms_per_step": dt_e2e * 1e3, "steps": e2e_steps,
                "timing": "host wall clock between device synchronisations, max over ranks (the leg includes the control-point stage at N=1 and host pivot generation)",
-               "cp_stage_ms": float(np.mean(cp_ms)) if cp_ms else None,
+               "cp_stage_ms": float(np.mean(cp_ms)) if cp_ms else None, "cp_stage_ms_per_step": [round(x, 2) for x in cp_ms],
                "mean_support": qual}
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1) + parity verdict on the measured scene ---------

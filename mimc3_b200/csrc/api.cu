@@ -192,6 +192,7 @@ void mimc3cu_destroy(mimc3cu_ctx *ctx) {
         for (auto &b : p.bins) if (b.lists) cudaFree(b.lists);
         if (p.last_use) cudaEventDestroy(p.last_use);
     }
+    if (ctx->cp_pool) cudaFree(ctx->cp_pool);
     if (ctx->statbuf) cudaFree(ctx->statbuf);
     if (ctx->overflow_list) cudaFree(ctx->overflow_list);
     if (ctx->node_uv) cudaFree(ctx->node_uv);

@@ -91,6 +91,10 @@ struct mimc3cu_ctx {
     int matcher = 0;                   // 0 auto, 1 force the general FP64 kernel, 2 require v2
     int last_matcher = 0;              // which kernel family the last match call used (1 general, 2 exact-FP32)
 
+    // device buffers of the control-point stage (cp.cu), grow-only
+    void *cp_pool = nullptr;
+    size_t cp_pool_bytes = 0;
+
     // postprocess state kept for mimc3cu_postprocess_stage
     struct Post *post = nullptr;
     BandComm *comm = nullptr;

@@ -19,6 +19,8 @@
 #include <math_constants.h>
 #include <stdlib.h>
 
+#include <chrono>
+
 #include "common.cuh"
 
 namespace {
@@ -144,12 +146,36 @@ __global__ void __launch_bounds__(kT) cp_apply_shift_kernel(float *__restrict__ 
     }
 }
 
+// Device buffers of one call come out of a pool the context keeps (grow-only): cudaMalloc / cudaFree per call cost a
+// device-wide synchronisation each and made the stage take 75 ... 240 ms from call to call.  A buffer is a slice of the
+// pool; the pool is rewound when a group of buffers goes out of use.
+struct CpPool {
+    mimc3cu_ctx *ctx;
+    size_t used = 0;
+    explicit CpPool(mimc3cu_ctx *c) : ctx(c) {}
+    cudaError_t reserve(size_t bytes) {     // only while no slice is in use (the pool may move)
+        used = 0;
+        if (bytes <= ctx->cp_pool_bytes) return cudaSuccess;
+        cudaStreamSynchronize(ctx->stream);
+        if (ctx->cp_pool) cudaFree(ctx->cp_pool);
+        ctx->cp_pool = nullptr; ctx->cp_pool_bytes = 0;
+        const size_t want = bytes + bytes / 4;
+        cudaError_t e = cudaMalloc(&ctx->cp_pool, want);
+        if (e == cudaSuccess) ctx->cp_pool_bytes = want;
+        return e;
+    }
+    void *take(size_t bytes) {
+        void *p = (char *)ctx->cp_pool + used;
+        used += (bytes + 255) & ~(size_t)255;
+        return used <= ctx->cp_pool_bytes ? p : nullptr;
+    }
+};
 struct DevBuf {
     void *p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
     template <typename T> T *as() { return (T *)p; }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+    cudaError_t take(CpPool &pool, size_t bytes) { p = pool.take(bytes ? bytes : 1); return p ? cudaSuccess : cudaErrorMemoryAllocation; }
 };
+inline size_t pad256(size_t b) { return (b + 255) & ~(size_t)255; }
 
 }  // namespace
 
@@ -158,6 +184,7 @@ int cp_get_offset_image(mimc3cu_ctx *ctx, Image *i0, Image *i1, const double *xy
                         uint8_t *flag_cp, int32_t *result, int32_t *num_cp_found) {
     const int H = i0->H, W = i0->W;
     cudaStream_t st = ctx->stream;
+    CpPool pool(ctx);
     *result = -1;
     if (num_cp_found) *num_cp_found = 0;
     const int ocw2 = p->vec_ocw[2];
@@ -169,6 +196,15 @@ int cp_get_offset_image(mimc3cu_ctx *ctx, Image *i0, Image *i1, const double *xy
     if ((float)n * p->ratio_cp > (float)p->num_cp_max) num_cp = p->num_cp_max;
     else num_cp = (int32_t)((float)n * p->ratio_cp);
 
+    // wall-clock checkpoints on stderr with MIMC3CU_CP_TIMING=1 (development aid)
+    const bool cp_timing = getenv("MIMC3CU_CP_TIMING") != nullptr;
+    auto cp_t0 = std::chrono::steady_clock::now();
+    auto checkpoint = [&](const char *what) {
+        if (!cp_timing) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[mimc3cu cp] %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(now - cp_t0).count());
+        cp_t0 = now;
+    };
     // candidates: slow nodes (:71-83) ...
     std::vector<int32_t> cand;
     for (int32_t g = 0; g < n; g++) {
@@ -183,13 +219,17 @@ int cp_get_offset_image(mimc3cu_ctx *ctx, Image *i0, Image *i1, const double *xy
             uv[k].y = (int32_t)xyuvav[6 * (size_t)cand[k] + 3];
         }
         DevBuf d_uv, d_cnt;
-        CU_CHECK(ctx, d_uv.alloc(sizeof(int2) * uv.size()));
-        CU_CHECK(ctx, d_cnt.alloc(sizeof(int) * uv.size()));
+        CU_CHECK(ctx, pool.reserve(pad256(sizeof(int2) * uv.size()) + pad256(sizeof(int) * uv.size())));
+        CU_CHECK(ctx, d_uv.take(pool, sizeof(int2) * uv.size()));
+        CU_CHECK(ctx, d_cnt.take(pool, sizeof(int) * uv.size()));
         CU_CHECK(ctx, cudaMemcpyAsync(d_uv.p, uv.data(), sizeof(int2) * uv.size(), cudaMemcpyHostToDevice, st));
         CU_CHECK(ctx, cudaMemsetAsync(d_cnt.p, 0, sizeof(int) * uv.size(), st));
         // the table is needed by the matcher anyway (raw-pair attempts) and is cached with the image
-        if (ctx->matcher != 1) { if (int rc = ensure_image_sat(ctx, i0)) return rc; }
-        if (ctx->matcher != 1 && i0->exact_class && i0->sat_valid)
+        // (only for very long candidate lists -- 8-px node spacing -- where the per-candidate pixel loop costs seconds; at
+        // C2 size the loop takes 10 ms and the table would have to be built before the matcher needs it)
+        const bool use_sat = ctx->matcher != 1 && uv.size() > (size_t)4000000 && !getenv("MIMC3CU_CP_NO_SAT");
+        if (use_sat) { if (int rc = ensure_image_sat(ctx, i0)) return rc; }
+        if (use_sat && i0->exact_class && i0->sat_valid)
             cp_nullcount_sat_kernel<<<(unsigned)((uv.size() + kT - 1) / kT), kT, 0, st>>>((const ulonglong2 *)i0->sat, H, W, d_uv.as<int2>(),
                                                                                       (int)uv.size(), ocw2, d_cnt.as<int>());
         else
@@ -205,6 +245,7 @@ int cp_get_offset_image(mimc3cu_ctx *ctx, Image *i0, Image *i1, const double *xy
             if (!(cnt[k] > thres_numpx)) keep.push_back(cand[k]);
         cand.swap(keep);
     }
+    checkpoint("candidates + null counts");
     const int32_t num_cand = (int32_t)cand.size();
     if (num_cand < p->num_cp_min) return 0;   // :130-135 (result stays -1)
     if (num_cp > num_cand) num_cp = (int32_t)((float)num_cand * 0.75);   // :137-141 (float * double literal)
@@ -223,6 +264,7 @@ int cp_get_offset_image(mimc3cu_ctx *ctx, Image *i0, Image *i1, const double *xy
         cand.swap(out);
     }
 
+    checkpoint("random permutation");
     // segments (:183-194)
     const int32_t num_segment = (num_cand < p->num_cp_min) ? 1 : num_cand / num_cp;
     std::vector<int32_t> seg(num_segment + 1);
@@ -235,26 +277,26 @@ int cp_get_offset_image(mimc3cu_ctx *ctx, Image *i0, Image *i1, const double *xy
     for (int a = -R; a <= R; a++)
         for (int b = -R; b <= R; b++) { piv.push_back(a); piv.push_back(b); }
     const int P = (int)piv.size() / 2;
-    DevBuf d_piv, d_kern;
-    CU_CHECK(ctx, d_piv.alloc(sizeof(int32_t) * piv.size()));
-    CU_CHECK(ctx, cudaMemcpyAsync(d_piv.p, piv.data(), sizeof(int32_t) * piv.size(), cudaMemcpyHostToDevice, st));
     float kall[15];
     memcpy(kall, k1x3, 3 * sizeof(float)); memcpy(kall + 3, k3x1, 3 * sizeof(float)); memcpy(kall + 6, k3x3, 9 * sizeof(float));
-    CU_CHECK(ctx, d_kern.alloc(sizeof(kall)));
-    CU_CHECK(ctx, cudaMemcpyAsync(d_kern.p, kall, sizeof(kall), cudaMemcpyHostToDevice, st));
     const int kh[3] = {1, 3, 3}, kw[3] = {3, 1, 3}, koff[3] = {0, 3, 6};
-
     int32_t max_sub = 0;
     for (int32_t c = 0; c < num_segment; c++) max_sub = std::max(max_sub, seg[c + 1] - seg[c]);
-    DevBuf d_uv, d_tiles, d_mins, d_shift, d_dp, d_mvn, d_ncl;
-    CU_CHECK(ctx, d_uv.alloc(sizeof(int2) * (size_t)max_sub));
-    CU_CHECK(ctx, d_tiles.alloc(sizeof(float) * 2 * (size_t)max_sub * T * T));
-    CU_CHECK(ctx, d_mins.alloc(sizeof(float) * 2 * (size_t)max_sub));
-    CU_CHECK(ctx, d_shift.alloc(sizeof(float) * 2 * (size_t)max_sub));
-    CU_CHECK(ctx, d_dp.alloc(sizeof(float) * 16 * (size_t)max_sub * 3));
-    CU_CHECK(ctx, d_mvn.alloc(sizeof(float) * (size_t)max_sub * 16 * 5));
-    CU_CHECK(ctx, d_ncl.alloc(sizeof(int32_t) * (size_t)max_sub));
+    const size_t ms = (size_t)max_sub;
+    const size_t sizes[9] = {sizeof(int32_t) * piv.size(), sizeof(kall), sizeof(int2) * ms, sizeof(float) * 2 * ms * T * T,
+                             sizeof(float) * 2 * ms, sizeof(float) * 2 * ms, sizeof(float) * 16 * ms * 3,
+                             sizeof(float) * ms * 16 * 5, sizeof(int32_t) * ms};
+    size_t total = 0;
+    for (size_t b : sizes) total += pad256(b ? b : 1);
+    // the candidate buffers of the step above are no longer in use: the pool is rewound (and may grow) here
+    CU_CHECK(ctx, pool.reserve(total));
+    DevBuf d_piv, d_kern, d_uv, d_tiles, d_mins, d_shift, d_dp, d_mvn, d_ncl;
+    DevBuf *bufs[9] = {&d_piv, &d_kern, &d_uv, &d_tiles, &d_mins, &d_shift, &d_dp, &d_mvn, &d_ncl};
+    for (int b = 0; b < 9; b++) CU_CHECK(ctx, bufs[b]->take(pool, sizes[b]));
+    CU_CHECK(ctx, cudaMemcpyAsync(d_piv.p, piv.data(), sizeof(int32_t) * piv.size(), cudaMemcpyHostToDevice, st));
+    CU_CHECK(ctx, cudaMemcpyAsync(d_kern.p, kall, sizeof(kall), cudaMemcpyHostToDevice, st));
 
+    checkpoint("buffers");
     float sduv[2] = {0.0f, 0.0f};
     int32_t num_cp_current = 0;
     bool ok = false;
@@ -313,6 +355,7 @@ int cp_get_offset_image(mimc3cu_ctx *ctx, Image *i0, Image *i1, const double *xy
                     num_cp_current++;
                 }
             }
+        checkpoint("segment");
         if (num_cp <= num_cp_current) { ok = true; break; }
     }
     if (num_cp_found) *num_cp_found = num_cp_current;

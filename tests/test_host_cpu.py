@@ -97,3 +97,49 @@ def test_get_uv_pivot_multithreaded_grid(orc):
     off2, piv2 = lib.get_uv_pivot(x2, sc.dt, p.mpp, 40, 1536, 1536)
     off2_o, piv2_o = orc.get_uv_pivot(x2, sc.dt, p.mpp, 40, 1536, 1536)
     assert np.array_equal(off2, off2_o) and np.array_equal(piv2, piv2_o)
+
+
+def test_reference_arm_of_the_bench_runs_without_the_cuda_library(tmp_path):
+    """`bench.py --impl reference` is the reference's own CPU implementation only: it must work where libmimc3cu.so cannot
+    even be found, take all host threads although the launcher exports OMP_NUM_THREADS=1 (torchrun does), and print the
+    contract's JSON line."""
+    import json
+    import subprocess
+    import sys
+    import oracle
+    if not os.path.exists(oracle.REF_SO):
+        pytest.skip("oracle/_ref/libmimc3ref.so not present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MIMC3CU_LIB=str(tmp_path / "no_such_library.so"), OMP_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "c1", "--steps", "1",
+                        "--warmup", "0", "--cpu-sample-nodes", "102"], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "nodes/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cp_stage_ms"] > 0 and line["cp_offset"] == [2, -1]
+
+
+def test_bench_reference_sample_returns_the_references_dp(orc):
+    """The parity verdict of the bench line compares the GPU dp with what cpu_reference_sample keeps: it must be the
+    reference's matching_ncc_dlc_2 output of the sampled nodes, with the sign flip main applies to the swapped passes."""
+    import oracle
+    import bench
+    from mimc3_b200 import synth
+    if not os.path.exists(oracle.REF_SO):
+        pytest.skip("oracle/_ref/libmimc3ref.so not present")
+    sc = synth.make_scene(H=384, W=384, dtype="u8", spacing=31, seed=8, peak_px=4.0)
+    i0, i1 = sc.i0.numpy(), sc.i1.numpy()
+    offset = np.array(sc.offset, np.int32)
+    res = bench.cpu_reference_sample(i0, i1, sc.xyuvav, sc.dimx, sc.dimy, sc.dt, offset, 2 * sc.dimx, keep_dp=True, with_cp=False)
+    idx = res["idx"]
+    assert res["dp"].shape == (32, len(idx), 3) and res["kind"] == "reference"
+    mpp = float(np.float32((sc.xyuvav[1, 0] - sc.xyuvav[0, 0]) / (sc.xyuvav[1, 2] - sc.xyuvav[0, 2])))
+    xs = np.ascontiguousarray(sc.xyuvav[idx])
+    off, piv = orc.get_uv_pivot(xs, sc.dt, mpp, 15, 384, 384)
+    fwd, _, _ = orc.match(i0, i1, xs, offset, off, piv, +1, 15)
+    swp, _, _ = orc.match(i1, i0, xs, -offset, off, piv, -1, 15)
+    a, b = res["dp"][2], fwd          # attempt 2 = raw pair, ocw 15, forward
+    assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)])
+    a, b = res["dp"][3], swp * np.array([-1, -1, 1], np.float32)
+    assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)])
