@@ -422,7 +422,8 @@ GMA_float *matching_ncc_dlc_2(GMA_float *i0, GMA_float *i1, GMA_double *xyuvav, 
     const int32_t K = num_dp > 0 ? num_dp : 32;
     if ((int32_t)g_attempts.size() >= K) g_attempts.clear();   // a new run of attempts over the same pair
     const int32_t slot = (int32_t)g_attempts.size();
-    GMA_float *out = GMA_float_create(n, 3);
+    // the kernels are enqueued first; the host array the driver gets back is allocated (and its pages touched) while
+    // they run -- at 16.6 M nodes the allocation and the page faults of a 200 MB array cost ~0.1 s per attempt
     for_devs([&](int d) {
         Dev &D = g_devs[d];
         DevImage &a = device_image(d, i0, 0), &b = device_image(d, i1, 0);
@@ -436,7 +437,13 @@ GMA_float *matching_ncc_dlc_2(GMA_float *i0, GMA_float *i1, GMA_double *xyuvav, 
         }
         float *dst = D.dp + (size_t)slot * D.n * 3;
         CK(mimc3cu_match_async(D.ctx, a.handle, b.handle, offset, ps->slot, sign, ocw, 0, dst, nullptr, nullptr), "matching_ncc_dlc_2", D.ctx);
-        CK(mimc3cu_memcpy_d2h(D.ctx, out->data + 3 * (size_t)D.g0, dst, sizeof(float) * 3 * (size_t)D.n), "memcpy_d2h", D.ctx);
+    });
+    GMA_float *out = GMA_float_create(n, 3);
+    parallel_for(n, [&](int32_t b, int32_t e) { memset(out->data + 3 * (size_t)b, 0, sizeof(float) * 3 * (size_t)(e - b)); });
+    for_devs([&](int d) {
+        Dev &D = g_devs[d];
+        const float *src = D.dp + (size_t)slot * D.n * 3;
+        CK(mimc3cu_memcpy_d2h(D.ctx, out->data + 3 * (size_t)D.g0, src, sizeof(float) * 3 * (size_t)D.n), "memcpy_d2h", D.ctx);
     });
     Attempt at;
     at.host = out;

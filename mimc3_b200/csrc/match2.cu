@@ -142,6 +142,14 @@ struct Cfg {
     // smallest chip only (+7 % at half-width 7; the row-per-lane pattern is uncoalesced and costs 10-20 % at 30 / 40,
     // even when the warps that idle during the previous node's replay do the loading)
     static constexpr bool DIRECT_CHIP = OCW == 7 && G == 32;
+#ifndef MIMC3CU_ASYNC
+#define MIMC3CU_ASYNC 9
+#endif
+    // staging by asynchronous 4-byte copies: bit 0 search area / bit 1 chip of the 128- and 256-thread groups,
+    // bit 2 search area at half-width 15, bit 3 at half-width 7 (32-thread groups)
+    static constexpr bool ASYNC_AREA = ((MIMC3CU_ASYNC & 1) && G >= 128) || ((MIMC3CU_ASYNC & 4) && G == 32 && OCW == 15) ||
+                                       ((MIMC3CU_ASYNC & 8) && G == 32 && OCW == 7);
+    static constexpr bool ASYNC_CHIP = ((MIMC3CU_ASYNC & 2) && G >= 128) || ((MIMC3CU_ASYNC & 16) && G == 32 && OCW == 15);
     static_assert(NSEG >= 1, "group too small for this chip");
     static_assert((L + 1) / 2 <= 16, "at most 16 pixels per FP32 accumulator");
 };
@@ -167,6 +175,32 @@ __device__ __forceinline__ void stage_rows(const float *__restrict__ src, int gs
 #pragma unroll
         for (int u = 0; u < DEPTH; u++)
             if (e + u * NT < total) dst[e + u * NT] = v[u];
+    }
+}
+
+// Same copy with asynchronous 4-byte global -> shared copies (LDGSTS): no register holds a pixel, so every load of the
+// thread is in flight at once instead of DEPTH at a time; pad columns are zero-filled by the copy itself (src-size 0).
+// The caller commits / waits (cp_async_wait_all) and then synchronises the group.
+__device__ __forceinline__ void cp_async4(float *dst, const float *src, bool ok) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    const int bytes = ok ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+template <int NT>
+__device__ __forceinline__ void stage_rows_async(const float *__restrict__ src, int gstride, float *dst, int spitch, int rows, int width,
+                                                 int tix) {
+    const int total = rows * spitch;
+    int y = tix / spitch, x = tix - y * spitch;
+    const int dy = NT / spitch, dx = NT - dy * spitch;
+#pragma unroll 4
+    for (int e = tix; e < total; e += NT) {
+        const bool ok = x < width;
+        cp_async4(dst + e, ok ? src + (size_t)y * gstride + x : src, ok);
+        x += dx; y += dy;
+        if (x >= spitch) { x -= spitch; y++; }
     }
 }
 
@@ -799,7 +833,10 @@ __global__ void __launch_bounds__(Cfg<OCW, G>::CTA, MINCTA) match2_kernel(const 
             load_chip_direct<OCW, G>(a, u0, v0, r, col0, len, chip);
         } else if (u0 - OCW >= 0 && v0 - OCW >= 0 && u0 + OCW < a.W && v0 + OCW < a.H) {
             const size_t first = (size_t)(v0 - OCW) * a.W + (u0 - OCW);
-            if (C::VEC && vec_ok && first >= 3 && first + (size_t)(S - 1) * a.W + S + 3 <= (size_t)a.H * a.W)
+            if (C::ASYNC_CHIP) {
+                stage_rows_async<G>(a.ref + first, a.W, sa, S, S, S, t);
+                cp_async_wait_all();
+            } else if (C::VEC && vec_ok && first >= 3 && first + (size_t)(S - 1) * a.W + S + 3 <= (size_t)a.H * a.W)
                 stage_rows_v4<G, 4>(a.ref + first, a.W, sa, S, S, S, t);
             else
                 stage_rows<G, 8>(a.ref + first, a.W, sa, S, S, S, t);
@@ -845,7 +882,9 @@ __global__ void __launch_bounds__(Cfg<OCW, G>::CTA, MINCTA) match2_kernel(const 
         if (su0 - dx2 >= 0 && sv0 - dy2 >= 0 && su0 - dx2 + Dx2 - 1 <= a.W && sv0 - dy2 + Dy2 - 1 <= a.H) {
             // written part entirely inside the image (the common case): no per-pixel bounds tests
             const size_t first = (size_t)(sv0 - dy2) * a.W + (su0 - dx2);
-            if (C::VEC && vec_ok && first >= 3 && first + (size_t)(Dy2 - 2) * a.W + Dx2 + 2 <= (size_t)a.H * a.W)
+            if (C::ASYNC_AREA)
+                stage_rows_async<G>(a.srch + first, a.W, sa, pitch, Dy2 - 1, Dx2 - 1, t);   // waited for below, after the table reset
+            else if (C::VEC && vec_ok && first >= 3 && first + (size_t)(Dy2 - 2) * a.W + Dx2 + 2 <= (size_t)a.H * a.W)
                 stage_rows_v4<G, (G >= 128 ? 2 : 4)>(a.srch + first, a.W, sa, pitch, Dy2 - 1, Dx2 - 1, t);   // the chip pixels are live here: fewer loads in flight
             else
                 stage_rows<G, 8>(a.srch + first, a.W, sa, pitch, Dy2 - 1, Dx2 - 1, t);
@@ -868,6 +907,7 @@ __global__ void __launch_bounds__(Cfg<OCW, G>::CTA, MINCTA) match2_kernel(const 
             ctl.geo = {g, P, su0, sv0, dx2, dy2, Dx2, Dy2, cw, ch, sa_elems, cell_elems};
             ctl.m = 0; ctl.nblk = 0;
         }
+        if (C::ASYNC_AREA) cp_async_wait_all();
         gsync<G>();
         if (!ctl.valid) {   // investigate_valid_grid: the search area was staged for nothing (rare)
             if (t == 0) {
